@@ -1,0 +1,302 @@
+// apx_api.cu — the C ABI (include/apx.h): argument checking, workspace carving, TMA descriptor
+// encoding and the host-side sequencing of the kernels for one adapter site and for the AudioMAE encoder.
+#include "apx_internal.h"
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace apx {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_impl{APX_IMPL_TC};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+int current_impl() { return g_impl.load(std::memory_order_relaxed); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libapx.so has no link-time dependency
+// on libcuda.so, so it loads (and its symbols can be checked) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    APX_REQUIRE(fn != nullptr, APX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) gstr[i] = strides_bytes[i];
+    }
+    const CUtensorMapDataType dt = dtype == APX_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = fn(tm, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    APX_REQUIRE(r == CUDA_SUCCESS, APX_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return APX_OK;
+}
+
+// ---- context cache layout: [K natural][V natural][packed K / V^T tiles] ---------------------------
+struct CtxCacheLayout {
+    size_t nat_bytes;    // one natural [Bc, L, C] tensor, 256-aligned
+    size_t tiles_off;    // offset of the packed tiles
+    size_t total;
+};
+static CtxCacheLayout ctx_cache_layout(int Bc, int Lt, int La, int C, int H) {
+    CtxCacheLayout l;
+    l.nat_bytes = align_up(static_cast<size_t>(Bc) * (Lt + La) * C * 2, 256);
+    l.tiles_off = 2 * l.nat_bytes;
+    const KvPackGeom g = kv_pack_geom(Lt, La, C, H);
+    l.total = l.tiles_off + static_cast<size_t>(Bc) * H * g.bytes_per_bh;
+    return l;
+}
+
+// rows < Lt of every batch element come from the text product, the others from the adapter product
+__global__ void kv_merge_kernel(const uint4* __restrict__ kt, const uint4* __restrict__ vt, const uint4* __restrict__ ka,
+                                const uint4* __restrict__ va, uint4* __restrict__ k, uint4* __restrict__ v, int L, int Lt,
+                                int C8, size_t total) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int l = static_cast<int>((i / C8) % L);
+        k[i] = l < Lt ? kt[i] : ka[i];
+        v[i] = l < Lt ? vt[i] : va[i];
+    }
+}
+
+}  // namespace apx
+
+using namespace apx;
+
+extern "C" {
+
+const char* apx_last_error(void) { return g_err; }
+int apx_version(void) { return 1; }
+uint64_t apx_launch_count(void) { return g_launches.load(); }
+
+int apx_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        set_error(APX_ECUDA, "no CUDA device");
+        return 0;
+    }
+    if (p.major != 10) {
+        set_error(APX_EUNSUPPORTED, "device '%s' is compute %d.%d; libapx is built for sm_100a only", p.name, p.major, p.minor);
+        return 0;
+    }
+    return 1;
+}
+
+int apx_set_impl(int impl) {
+    APX_REQUIRE(impl == APX_IMPL_TC || impl == APX_IMPL_SIMT, APX_EINVAL, "apx_set_impl: unknown impl %d", impl);
+    g_impl.store(impl);
+    return APX_OK;
+}
+int apx_get_impl(void) { return current_impl(); }
+
+int apx_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+               int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
+               void* stream) {
+    APX_REQUIRE(A && W && out, APX_EINVAL, "apx_linear: null pointer");
+    APX_REQUIRE(out_dtype == APX_F16 || out_dtype == APX_BF16 || out_dtype == APX_F32, APX_EINVAL,
+                "apx_linear: out_dtype %d", out_dtype);
+    APX_REQUIRE(epilogue == APX_EPI_NONE || epilogue == APX_EPI_GELU, APX_EINVAL, "apx_linear: epilogue %d", epilogue);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (current_impl() == APX_IMPL_SIMT)
+        return gemm_simt(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue, st);
+    return gemm_tc(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue, st);
+}
+
+int apx_attention(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V,
+                  int64_t v_bs, int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int H, int d, int L,
+                  int L0, float w0, float w1, int dtype, void* stream) {
+    APX_REQUIRE(Q && K && V && O, APX_EINVAL, "apx_attention: null pointer");
+    return attention_simt(Q, q_bs, q_rs, K, k_bs, k_rs, V, v_bs, v_rs, O, o_bs, o_rs, B, S, H, d, L, L0, w0, w1, dtype,
+                          static_cast<cudaStream_t>(stream));
+}
+
+size_t apx_ctx_kv_bytes(int Bc, int Lt, int La, int C, int H) {
+    if (Bc <= 0 || Lt < 0 || La < 0 || C <= 0 || H <= 0 || C % H) return 0;
+    return ctx_cache_layout(Bc, Lt, La, C, H).total;
+}
+size_t apx_ctx_kv_workspace_bytes(int Bc, int Lt, int La, int C) {
+    return 4 * align_up(static_cast<size_t>(Bc) * (Lt + La) * C * 2, 256);
+}
+
+int apx_ctx_kv(const void* ctx, const void* Wk, const void* Wv, const void* Wk_ip, const void* Wv_ip, void* cache,
+               int Bc, int Lt, int La, int Dctx, int C, int H, int dtype, void* workspace, size_t workspace_bytes,
+               void* stream) {
+    APX_REQUIRE(ctx && Wk && Wv && Wk_ip && Wv_ip && cache && workspace, APX_EINVAL, "apx_ctx_kv: null pointer");
+    APX_REQUIRE(Bc > 0 && Lt >= 0 && La >= 0 && Lt + La > 0 && C > 0 && H > 0 && C % H == 0, APX_EINVAL,
+                "apx_ctx_kv: bad shape Bc=%d Lt=%d La=%d C=%d H=%d", Bc, Lt, La, C, H);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_ctx_kv: dtype %d", dtype);
+    APX_REQUIRE(C % 8 == 0, APX_EUNSUPPORTED, "apx_ctx_kv: C=%d must be a multiple of 8", C);
+    APX_REQUIRE(workspace_bytes >= apx_ctx_kv_workspace_bytes(Bc, Lt, La, C), APX_EWORKSPACE,
+                "apx_ctx_kv: workspace %zu < %zu", workspace_bytes, apx_ctx_kv_workspace_bytes(Bc, Lt, La, C));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L = Lt + La, M = Bc * L;
+    const CtxCacheLayout lay = ctx_cache_layout(Bc, Lt, La, C, H);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    void* kt = ws;
+    void* vt = ws + lay.nat_bytes;
+    void* ka = ws + 2 * lay.nat_bytes;
+    void* va = ws + 3 * lay.nat_bytes;
+    // Both weight sets are applied to every context row (one GEMM each over M = Bc*(Lt+La) rows); the merge /
+    // pack kernels then pick text rows from the to_k/to_v products and audio rows from the to_k_ip/to_v_ip ones.
+    const void* Ws[4] = {Wk, Wv, Wk_ip, Wv_ip};
+    void* outs[4] = {kt, vt, ka, va};
+    for (int i = 0; i < 4; ++i) {
+        int rc = apx_linear(ctx, Dctx, Ws[i], Dctx, nullptr, nullptr, 0, outs[i], C, M, C, Dctx, dtype, dtype,
+                            APX_EPI_NONE, stream);
+        if (rc) return rc;
+    }
+    uint8_t* cb = static_cast<uint8_t*>(cache);
+    const size_t total16 = static_cast<size_t>(M) * C / 8;
+    const int blocks = static_cast<int>(std::min<size_t>((total16 + 255) / 256, 148 * 8));
+    kv_merge_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint4*>(kt), static_cast<const uint4*>(vt),
+                                            static_cast<const uint4*>(ka), static_cast<const uint4*>(va),
+                                            reinterpret_cast<uint4*>(cb), reinterpret_cast<uint4*>(cb + lay.nat_bytes), L,
+                                            Lt, C / 8, total16);
+    APX_LAUNCH_CHECK("kv_merge_kernel");
+    return kv_pack(kt, vt, ka, va, cb + lay.tiles_off, Bc, Lt, La, C, H, dtype, st);
+}
+
+size_t apx_ipattn_workspace_bytes(int Bc, int S, int C) {
+    return 2 * align_up(static_cast<size_t>(Bc) * S * C * 2, 256);
+}
+
+int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const float* bo, void* Y, int Bc,
+                   int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    APX_REQUIRE(X && Wq && cache && Wo && Y && workspace, APX_EINVAL, "apx_ipattn_fwd: null pointer");
+    APX_REQUIRE(Bc > 0 && S > 0 && C > 0 && H > 0 && C % H == 0 && Lt >= 0 && La >= 0 && Lt + La > 0, APX_EINVAL,
+                "apx_ipattn_fwd: bad shape Bc=%d S=%d C=%d H=%d Lt=%d La=%d", Bc, S, C, H, Lt, La);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_ipattn_fwd: dtype %d", dtype);
+    APX_REQUIRE(workspace_bytes >= apx_ipattn_workspace_bytes(Bc, S, C), APX_EWORKSPACE,
+                "apx_ipattn_fwd: workspace %zu < %zu", workspace_bytes, apx_ipattn_workspace_bytes(Bc, S, C));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int M = Bc * S, d = C / H, L = Lt + La;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    void* q = ws;
+    void* o = ws + align_up(static_cast<size_t>(M) * C * 2, 256);
+    const CtxCacheLayout lay = ctx_cache_layout(Bc, Lt, La, C, H);
+    const uint8_t* cb = static_cast<const uint8_t*>(cache);
+
+    int rc = apx_linear(X, C, Wq, C, nullptr, nullptr, 0, q, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
+    if (rc) return rc;
+    if (current_impl() == APX_IMPL_SIMT) {
+        rc = attention_simt(q, static_cast<int64_t>(S) * C, C, cb, static_cast<int64_t>(L) * C, C, cb + lay.nat_bytes,
+                            static_cast<int64_t>(L) * C, C, o, static_cast<int64_t>(S) * C, C, Bc, S, H, d, L, Lt, 1.0f,
+                            ap_scale, dtype, st);
+    } else {
+        rc = ipattn_core_tc(q, cb + lay.tiles_off, o, Bc, S, C, H, Lt, La, ap_scale, dtype, st);
+    }
+    if (rc) return rc;
+    return apx_linear(o, C, Wo, C, bo, nullptr, 0, Y, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
+}
+
+// ---- AudioMAE -----------------------------------------------------------------------------------
+int apx_patch_embed(const float* mel, const float* patch_wT, const float* patch_b, const float* pos_embed,
+                    const float* cls_token, float* x, int B, void* stream) {
+    APX_REQUIRE(mel && patch_wT && patch_b && pos_embed && cls_token && x, APX_EINVAL, "apx_patch_embed: null pointer");
+    return patch_embed(mel, patch_wT, patch_b, pos_embed, cls_token, x, B, static_cast<cudaStream_t>(stream));
+}
+int apx_layernorm(const float* x, const float* w, const float* b, void* y, int rows, int cols, float eps, int out_dtype,
+                  void* stream) {
+    APX_REQUIRE(x && w && b && y, APX_EINVAL, "apx_layernorm: null pointer");
+    APX_REQUIRE(out_dtype == APX_F16 || out_dtype == APX_BF16 || out_dtype == APX_F32, APX_EINVAL,
+                "apx_layernorm: out_dtype %d", out_dtype);
+    return layernorm(x, w, b, y, rows, cols, eps, out_dtype, static_cast<cudaStream_t>(stream));
+}
+int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_pool, void* stream) {
+    APX_REQUIRE(xn && emb && B > 0, APX_EINVAL, "apx_pool_tokens: bad argument");
+    return pool_tokens(xn, emb, B, time_pool, freq_pool, static_cast<cudaStream_t>(stream));
+}
+
+struct MaeWorkspace {
+    size_t x, xn, qkv, att, hid, xf, total;
+};
+static MaeWorkspace mae_ws(int B) {
+    const size_t rows = static_cast<size_t>(B) * 513;
+    MaeWorkspace w;
+    size_t off = 0;
+    w.x = off;   off += align_up(rows * 768 * 4, 256);
+    w.xn = off;  off += align_up(rows * 768 * 2, 256);
+    w.qkv = off; off += align_up(rows * 2304 * 2, 256);
+    w.att = off; off += align_up(rows * 768 * 2, 256);
+    w.hid = off; off += align_up(rows * 3072 * 2, 256);
+    w.xf = off;  off += align_up(rows * 768 * 4, 256);
+    w.total = off;
+    return w;
+}
+size_t apx_audiomae_workspace_bytes(int B) { return B > 0 ? mae_ws(B).total : 0; }
+
+int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w, float* emb, int B, int time_pool, int freq_pool,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    APX_REQUIRE(mel && w && emb && workspace && w->blocks, APX_EINVAL, "apx_audiomae_fwd: null pointer");
+    APX_REQUIRE(B > 0, APX_EINVAL, "apx_audiomae_fwd: B=%d", B);
+    APX_REQUIRE(w->embed == 768 && w->heads == 12 && w->mlp == 3072 && w->depth > 0, APX_EUNSUPPORTED,
+                "apx_audiomae_fwd: only the ViT-B geometry (768/12/3072) is implemented, got %d/%d/%d", w->embed,
+                w->heads, w->mlp);
+    APX_REQUIRE(w->wdtype == APX_F16 || w->wdtype == APX_BF16, APX_EUNSUPPORTED, "apx_audiomae_fwd: wdtype %d", w->wdtype);
+    const MaeWorkspace ws = mae_ws(B);
+    APX_REQUIRE(workspace_bytes >= ws.total, APX_EWORKSPACE, "apx_audiomae_fwd: workspace %zu < %zu", workspace_bytes,
+                ws.total);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float* x = reinterpret_cast<float*>(base + ws.x);
+    void* xn = base + ws.xn;
+    uint16_t* qkv = reinterpret_cast<uint16_t*>(base + ws.qkv);
+    void* att = base + ws.att;
+    void* hid = base + ws.hid;
+    float* xf = reinterpret_cast<float*>(base + ws.xf);
+    const int rows = B * 513, dt = w->wdtype;
+    const float eps = 1e-6f;  // partial(nn.LayerNorm, eps=1e-6): audio_encoder/models_mae.py:698
+    int rc;
+#define APX_STEP(call) do { rc = (call); if (rc) return rc; } while (0)
+    APX_STEP(apx_patch_embed(mel, w->patch_wT, w->patch_b, w->pos_embed, w->cls_token, x, B, stream));
+    for (int l = 0; l < w->depth; ++l) {
+        const apx_vit_block& k = w->blocks[l];
+        // x += proj(attn(LN1(x)))
+        APX_STEP(apx_layernorm(x, k.ln1_w, k.ln1_b, xn, rows, 768, eps, dt, stream));
+        APX_STEP(apx_linear(xn, 768, k.qkv_w, 768, k.qkv_b, nullptr, 0, qkv, 2304, rows, 2304, 768, dt, dt, APX_EPI_NONE, stream));
+        APX_STEP(apx_attention(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304,
+                               att, 513LL * 768, 768, B, 513, 12, 64, 513, 513, 1.0f, 0.0f, dt, stream));
+        APX_STEP(apx_linear(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, stream));
+        // x += fc2(GELU(fc1(LN2(x))))
+        APX_STEP(apx_layernorm(x, k.ln2_w, k.ln2_b, xn, rows, 768, eps, dt, stream));
+        APX_STEP(apx_linear(xn, 768, k.fc1_w, 768, k.fc1_b, nullptr, 0, hid, 3072, rows, 3072, 768, dt, dt, APX_EPI_GELU, stream));
+        APX_STEP(apx_linear(hid, 3072, k.fc2_w, 3072, k.fc2_b, x, 768, x, 768, rows, 768, 3072, dt, APX_F32, APX_EPI_NONE, stream));
+    }
+    APX_STEP(apx_layernorm(x, w->norm_w, w->norm_b, xf, rows, 768, eps, APX_F32, stream));
+    APX_STEP(apx_pool_tokens(xf, emb, B, time_pool, freq_pool, stream));
+#undef APX_STEP
+    return APX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// apx_internal.h — declarations shared by the translation units of libapx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/apx.h"
+
+namespace apx {
+
+// ---- error plumbing (thread-local message, integer codes across the ABI) -------------
+int  set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define APX_REQUIRE(cond, code, ...)                                 \
+    do {                                                             \
+        if (!(cond)) return ::apx::set_error((code), __VA_ARGS__);   \
+    } while (0)
+
+#define APX_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::apx::set_error(APX_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                    __FILE__, __LINE__);                                            \
+    } while (0)
+
+#define APX_LAUNCH_CHECK(name)                                                                         \
+    do {                                                                                               \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return ::apx::set_error(APX_ECUDA, "launch of %s failed: %s", (name), cudaGetErrorString(_e)); \
+        ::apx::count_launch();                                                                         \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int    ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int    elem_size(int dtype) { return dtype == APX_F32 ? 4 : 2; }
+
+// ---- TMA descriptor encoding (driver entry point resolved at run time; no -lcuda) ------
+int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle128);
+
+// ---- tcgen05 kernels --------------------------------------------------------------------
+int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+            int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
+            cudaStream_t st);
+
+// Packed per-(batch, head) K / V^T tiles in UMMA no-swizzle K-major core-matrix order.
+struct KvPackGeom {
+    int Lt, La, Lt_pad, La_pad, L_pad, d, d_pad, H, C;
+    size_t k_tile_bytes, v_tile_bytes, bytes_per_bh;
+};
+KvPackGeom kv_pack_geom(int Lt, int La, int C, int H);
+
+int ipattn_core_tc(const void* Q, const void* cache, void* O, int Bc, int S, int C, int H, int Lt, int La,
+                   float ap_scale, int dtype, cudaStream_t st);
+int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void* cache, int Bc, int Lt, int La,
+            int C, int H, int dtype, cudaStream_t st);
+
+// ---- CUDA-core kernels --------------------------------------------------------------------
+int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+              int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
+              cudaStream_t st);
+int attention_simt(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs,
+                   const void* V, int64_t v_bs, int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S,
+                   int H, int d, int L, int L0, float w0, float w1, int dtype, cudaStream_t st);
+int patch_embed(const float* mel, const float* pwT, const float* pb, const float* pos, const float* cls, float* x,
+                int B, cudaStream_t st);
+int layernorm(const float* x, const float* w, const float* b, void* y, int rows, int cols, float eps, int out_dtype,
+              cudaStream_t st);
+int pool_tokens(const float* xn, float* emb, int B, int tp, int fp, cudaStream_t st);
+
+int current_impl();
+
+}  // namespace apx

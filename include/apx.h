@@ -1,0 +1,156 @@
+/*
+ * apx.h — C ABI of libapx.so, the sm_100a implementation of AP-adapter's hot path.
+ *
+ * Every entry point returns 0 on success and a non-zero APX_E* code on failure; the
+ * message is available from apx_last_error() (thread-local).  Nothing throws across
+ * the ABI, nothing falls back to a CPU or library path: an unsupported shape / dtype
+ * is an error.  All pointers are DEVICE pointers unless the name ends in `_host`.
+ * All launches go to the `stream` argument (a cudaStream_t passed as void*), perform
+ * no allocation and no host synchronisation, and are CUDA-graph capturable.
+ *
+ * Reference interfaces replaced (paths relative to the AP-adapter repository):
+ *   apx_ipattn_fwd        APadapter/ap_adapter/attention_processor.py:347-470
+ *                         (IPAttnProcessor2_0.__call__: to_q, two SDPAs, scale-add, to_out)
+ *   apx_ctx_kv            attention_processor.py:400-415,435-439 (to_k/to_v on the text rows,
+ *                         to_k_ip/to_v_ip on the audio rows; timestep-invariant, cached)
+ *   apx_linear            the nn.Linear dispatches on the path (attention_processor.py:387,457;
+ *                         timm Block qkv/proj/fc1/fc2 used by audio_encoder/models_mae.py:220-231)
+ *   apx_attention         F.scaled_dot_product_attention call sites
+ *                         (attention_processor.py:274,429,443; timm Attention in models_mae.py:566)
+ *   apx_audiomae_fwd      audio_encoder/AudioMAE.py:190-212 (forward) -> :37-55 ->
+ *                         audio_encoder/models_mae.py:548-570 (encoder) -> AudioMAE.py:148-182 (pool)
+ *   apx_patch_embed       audio_encoder/models_mae.py:19-44 (PatchEmbed_org) + :552,561-563
+ *   apx_layernorm         nn.LayerNorm(eps=1e-6) inside timm Block / models_mae.py:568
+ *   apx_pool_tokens       audio_encoder/AudioMAE.py:148-182 (drop CLS, (avg+max)/2 pooling)
+ */
+#ifndef APX_H_
+#define APX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------------------- */
+#define APX_OK            0
+#define APX_EINVAL        1   /* bad argument (null pointer, negative size, misalignment)   */
+#define APX_EUNSUPPORTED  2   /* shape / dtype outside what the sm_100a kernels implement    */
+#define APX_ECUDA         3   /* a CUDA runtime / driver call failed                         */
+#define APX_EWORKSPACE    4   /* caller-provided workspace too small                         */
+
+/* ---- element types ----------------------------------------------------------------- */
+#define APX_F16   0
+#define APX_BF16  1
+#define APX_F32   2
+
+/* ---- epilogue flags for apx_linear -------------------------------------------------- */
+#define APX_EPI_NONE      0
+#define APX_EPI_GELU      1   /* exact erf GELU, applied after the bias                      */
+
+/* ---- kernel families ---------------------------------------------------------------- */
+#define APX_IMPL_TC    0      /* tcgen05 + TMA + TMEM (product path)                         */
+#define APX_IMPL_SIMT  1      /* plain CUDA-core kernels: device-side cross-check for tests   */
+
+const char* apx_last_error(void);
+int         apx_version(void);            /* ABI version, bumps on any signature change   */
+int         apx_device_ok(void);          /* 1 iff the current device is compute 10.x      */
+int         apx_set_impl(int impl);       /* APX_IMPL_TC (default) or APX_IMPL_SIMT        */
+int         apx_get_impl(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches)     */
+uint64_t    apx_launch_count(void);
+
+/*
+ * Y[M,N] = act(A[M,K] · W[N,K]^T + bias[N]) + residual[M,N]
+ *   A, W      : `in_dtype` (APX_F16 | APX_BF16), row-major, K contiguous, lda/ldw in elements
+ *   bias      : fp32[N] or NULL
+ *   residual  : fp32[M,N] (ld = ldr) or NULL; may alias `out` when out_dtype == APX_F32
+ *   out       : `out_dtype` (APX_F16 | APX_BF16 | APX_F32), ld = ldo
+ * Requirements (tcgen05 path): K % 64 == 0, N % 64 == 0, 16-byte aligned rows.
+ */
+int apx_linear(const void* A, int64_t lda, const void* W, int64_t ldw,
+               const float* bias, const float* residual, int64_t ldr,
+               void* out, int64_t ldo,
+               int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
+               void* stream);
+
+/*
+ * Segmented multi-head attention on token-major tensors.
+ *   O[b,s,h,:] = w0 · softmax_{l<L0}(q·k_l / sqrt(d)) v_l  +  w1 · softmax_{L0<=l<L}(q·k_l / sqrt(d)) v_l
+ * With L0 == 0 or L0 == L this is plain softmax attention weighted by w1 / w0.
+ *   Q : [B, S, H*d] view, element strides (q_bs, q_rs), head h at column h*d
+ *   K, V : [B, L, H*d] views with their own strides; O : [B, S, H*d] view
+ * dtype APX_F16 | APX_BF16 for all four.  d % 8 == 0, d <= 96, L <= 544.
+ */
+int apx_attention(const void* Q, int64_t q_bs, int64_t q_rs,
+                  const void* K, int64_t k_bs, int64_t k_rs,
+                  const void* V, int64_t v_bs, int64_t v_rs,
+                  void* O, int64_t o_bs, int64_t o_rs,
+                  int B, int S, int H, int d, int L, int L0, float w0, float w1,
+                  int dtype, void* stream);
+
+/*
+ * Context K/V cache of one adapter site (timestep-invariant; build once per generation).
+ * ctx [Bc, Lt+La, Dctx] (`dtype`, contiguous); Wk/Wv [C, Dctx] are the UNet's attn2.to_k/to_v
+ * (applied to rows < Lt), Wk_ip/Wv_ip [C, Dctx] the adapter's to_k_ip/to_v_ip (rows >= Lt).
+ * `cache` receives apx_ctx_kv_bytes(...) bytes in the layout apx_ipattn_fwd consumes.
+ */
+size_t apx_ctx_kv_bytes(int Bc, int Lt, int La, int C, int H);
+int apx_ctx_kv(const void* ctx, const void* Wk, const void* Wv, const void* Wk_ip, const void* Wv_ip,
+               void* cache, int Bc, int Lt, int La, int Dctx, int C, int H, int dtype,
+               void* workspace, size_t workspace_bytes, void* stream);
+size_t apx_ctx_kv_workspace_bytes(int Bc, int Lt, int La, int C);
+
+/*
+ * One adapter site, one denoise step:
+ *   Y = ( SDPA(X Wq^T, K_t, V_t) + ap_scale · SDPA(X Wq^T, K_a, V_a) ) Wo^T + bo
+ * X, Y [Bc, S, C] contiguous `dtype`; Wq, Wo [C, C] `dtype`; bo fp32[C] or NULL;
+ * `cache` from apx_ctx_kv with identical (Bc, Lt, La, C, H).
+ * workspace: apx_ipattn_workspace_bytes(Bc, S, C) bytes.
+ */
+size_t apx_ipattn_workspace_bytes(int Bc, int S, int C);
+int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const float* bo,
+                   void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- AudioMAE encoder ---------------------------------------------------------------- */
+typedef struct apx_vit_block {
+    const float* ln1_w; const float* ln1_b;           /* fp32[768]                           */
+    const void*  qkv_w; const float* qkv_b;           /* [2304,768] wdtype, fp32[2304]       */
+    const void*  proj_w; const float* proj_b;         /* [768,768],  fp32[768]               */
+    const float* ln2_w; const float* ln2_b;
+    const void*  fc1_w; const float* fc1_b;           /* [3072,768], fp32[3072]              */
+    const void*  fc2_w; const float* fc2_b;           /* [768,3072], fp32[768]               */
+} apx_vit_block;
+
+typedef struct apx_vit_weights {
+    int depth, embed, heads, mlp;                      /* 12, 768, 12, 3072                   */
+    int wdtype;                                        /* APX_F16 | APX_BF16 (GEMM operands)  */
+    const float* patch_wT;                             /* fp32[256, 768]: Conv2d(1,768,16,16) weight
+                                                          viewed [768,256] and TRANSPOSED by the host  */
+    const float* patch_b;                              /* fp32[768]                            */
+    const float* pos_embed;                            /* fp32[513, 768]                       */
+    const float* cls_token;                            /* fp32[768]                            */
+    const float* norm_w; const float* norm_b;          /* final LayerNorm                      */
+    const apx_vit_block* blocks;                       /* host array of `depth` entries        */
+} apx_vit_weights;
+
+size_t apx_audiomae_workspace_bytes(int B);
+/* mel fp32 [B,1024,128] -> emb fp32 [B, 512/(tp*fp), 768]; LayerNorm eps = 1e-6. */
+int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w_host, float* emb,
+                     int B, int time_pool, int freq_pool,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* individual stages (also used by the parity tests) */
+int apx_patch_embed(const float* mel, const float* patch_wT, const float* patch_b,
+                    const float* pos_embed, const float* cls_token, float* x, int B, void* stream);
+int apx_layernorm(const float* x, const float* w, const float* b, void* y, int rows, int cols,
+                  float eps, int out_dtype, void* stream);
+/* xn: LayerNorm-ed tokens fp32 [B,513,768] -> emb fp32 [B, (64/tp)*(8/fp), 768] */
+int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_pool, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APX_H_ */
