@@ -1,0 +1,100 @@
+"""The oracle (CPU restatement) against outputs of the reference itself (tests/golden/, made by oracle/gen_golden.py).
+
+fp32 CPU on both sides: tolerance 1e-5 relative to max|ref| (SURVEY.md §8d "≤1e-5 (fp32 CPU restatement)").
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import audiomae_oracle as mae
+from oracle import cases, ipattn_oracle, ref_shims
+
+GOLD = cases.GOLDEN_DIR
+TOL = 1e-5
+
+
+def _rel(got: torch.Tensor, ref: np.ndarray) -> float:
+    ref = torch.from_numpy(ref)
+    return ((got - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.fixture(scope="module")
+def ip_gold():
+    return np.load(os.path.join(GOLD, "ipattn_reference.npz"))
+
+
+@pytest.mark.parametrize("name", list(cases.IPATTN_CASES))
+def test_ipattn_oracle_matches_reference_output(name, ip_gold):
+    c = cases.make_ipattn_case(name)
+    y = ipattn_oracle.ipattn_forward(c["x"], c["ctx"], c["wq"], c["wk"], c["wv"], c["wk_ip"], c["wv_ip"], c["wo"], c["bo"],
+                                     c["heads"], c["num_tokens"], c["scale"])
+    y = y.reshape(-1, y.shape[-1])[:: cases.ROW_STRIDE.get(name, 1)]
+    assert y.shape == ip_gold[name].shape
+    assert _rel(y, ip_gold[name]) < TOL
+
+
+@pytest.mark.parametrize("name", list(cases.ATTN_CASES))
+def test_plain_attn_oracle_matches_reference_output(name, ip_gold):
+    c = cases.make_attn_case(name)
+    mask = None if c["mask"] is None else c["mask"].unsqueeze(1)  # (B,1,1,L): what the reference's .view() yields per head
+    y = ipattn_oracle.attn_forward(c["x"], c["ctx"], c["wq"], c["wk"], c["wv"], c["wo"], c["bo"], c["heads"], mask)
+    assert _rel(y.reshape(-1, y.shape[-1]), ip_gold["plain_" + name]) < TOL
+
+
+def test_text_only_context_gives_zero_audio_branch():
+    """With no audio tokens the second SDPA returns zeros (torch semantics), so ap_scale has no effect."""
+    c = cases.make_ipattn_case("text_only")
+    args = (c["x"], c["ctx"], c["wq"], c["wk"], c["wv"], c["wk_ip"], c["wv_ip"], c["wo"], c["bo"], c["heads"], c["num_tokens"])
+    assert torch.equal(ipattn_oracle.ipattn_forward(*args, 0.5), ipattn_oracle.ipattn_forward(*args, 3.0))
+
+
+@pytest.fixture(scope="module")
+def mae_gold():
+    return np.load(os.path.join(GOLD, "audiomae_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def mae_sd():
+    return cases.mae_state_dict()
+
+
+def test_sincos_table_matches_reference(mae_gold):
+    assert np.array_equal(mae.sincos_pos_embed()[0, ::57].numpy(), mae_gold["pos_embed_rows"])
+
+
+@pytest.mark.parametrize("tag", ["synth", "piano"])
+def test_audiomae_oracle_matches_reference_output(tag, mae_gold, mae_sd):
+    torch.set_num_threads(os.cpu_count() or 1)
+    mel = cases.make_mel() if tag == "synth" else torch.from_numpy(mae_gold["mel_piano_f16"]).float().unsqueeze(0)
+    with torch.no_grad():
+        rep = mae.encoder(mel.unsqueeze(1), mae_sd)
+    assert rep.shape == (1, 513, 768)
+    assert _rel(rep[0, ::8], mae_gold[f"{tag}_encoder_rows"]) < TOL
+    for tp, fp in cases.POOLS:
+        pooled = mae.pool(rep, tp, fp)
+        assert pooled.shape == (1, 512 // (tp * fp), 768)
+        sub = pooled[0, ::4] if pooled.shape[1] > 128 else pooled[0]
+        assert _rel(sub, mae_gold[f"{tag}_pool_{tp}x{fp}"]) < TOL
+
+
+def test_audiomae_forward_returns_embedding_and_ones(mae_sd):
+    emb, ones = mae.audiomae_forward(cases.make_mel(), {k: v for k, v in mae_sd.items()}, 8, 8, depth=1)
+    assert emb.shape == (1, 8, 768) and ones.shape == (1, 8) and bool((ones == 1).all())
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_against_live_reference_processor():
+    """When the reference tree is mounted, run it live on a fresh seed (not only the committed fixtures)."""
+    ap = ref_shims.load_attention_processor()
+    g = torch.Generator().manual_seed(123)
+    bc, s, c, h, lt, la = 2, 50, 256, 8, 8, 16
+    x, ctx = torch.randn(bc, s, c, generator=g), torch.randn(bc, lt + la, 768, generator=g)
+    attn = ref_shims.StubAttention(c, 768, h)
+    proc = ap.IPAttnProcessor2_0(hidden_size=c, name="t", cross_attention_dim=768, num_tokens=lt, scale=0.7)
+    with torch.no_grad():
+        y_ref = proc(attn, x, encoder_hidden_states=ctx)
+        y = ipattn_oracle.ipattn_forward(x, ctx, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, proc.to_k_ip.weight,
+                                         proc.to_v_ip.weight, attn.to_out[0].weight, attn.to_out[0].bias, h, lt, 0.7)
+    assert ((y - y_ref).abs().max() / y_ref.abs().max()).item() < TOL
