@@ -1,0 +1,190 @@
+"""ctypes binding of libapx.so (the C ABI declared in include/apx.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic step of the hot path runs in
+the hand-written sm_100a kernels behind this ABI.  There is no CPU or eager fallback — if the library is
+missing, or a tensor is not on a CUDA device, the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapx.so")
+
+APX_F16, APX_BF16, APX_F32 = 0, 1, 2
+APX_EPI_NONE, APX_EPI_GELU = 0, 1
+APX_IMPL_TC, APX_IMPL_SIMT = 0, 1
+
+# every symbol include/apx.h declares: (restype, argtypes)
+_P, _I, _L, _F, _Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+
+class VitBlock(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitWeights(Structure):
+    _fields_ = [("depth", c_int), ("embed", c_int), ("heads", c_int), ("mlp", c_int), ("wdtype", c_int),
+                ("patch_wT", c_void_p), ("patch_b", c_void_p), ("pos_embed", c_void_p), ("cls_token", c_void_p),
+                ("norm_w", c_void_p), ("norm_b", c_void_p), ("blocks", POINTER(VitBlock))]
+
+
+SYMBOLS = {
+    "apx_last_error": (c_char_p, []),
+    "apx_version": (_I, []),
+    "apx_device_ok": (_I, []),
+    "apx_set_impl": (_I, [_I]),
+    "apx_get_impl": (_I, []),
+    "apx_launch_count": (c_uint64, []),
+    "apx_linear": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "apx_attention": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
+    "apx_ctx_kv_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "apx_ctx_kv_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "apx_ctx_kv": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "apx_ipattn_workspace_bytes": (_Z, [_I, _I, _I]),
+    "apx_ipattn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "apx_audiomae_workspace_bytes": (_Z, [_I]),
+    "apx_audiomae_fwd": (_I, [_P, POINTER(VitWeights), _P, _I, _I, _I, _P, _Z, _P]),
+    "apx_audiomae_encode": (_I, [_P, POINTER(VitWeights), _P, _I, _P, _Z, _P]),
+    "apx_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "apx_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _I, _P]),
+    "apx_pool_tokens": (_I, [_P, _P, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class ApxError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libapx.so (built in-tree by `__graft_entry__.build()` / `make -C ap_adapter_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ApxError(
+                f"{LIB_PATH} not found: the sm_100a extension is not built (run `python -c 'import __graft_entry__ as g; "
+                "g.build()'`). ap_adapter_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError here == header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise ApxError(f"{what} failed (code {rc}): {load().apx_last_error().decode(errors='replace')}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float16:
+        return APX_F16
+    if dt == torch.bfloat16:
+        return APX_BF16
+    if dt == torch.float32:
+        return APX_F32
+    raise ApxError(f"unsupported dtype {dt}: the sm_100a kernels take float16 / bfloat16 operands")
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ApxError("ap_adapter_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ApxError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces: dict[tuple, torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
+    """A grow-only scratch buffer per (device, stream, tag).  Kernels on one stream are serialised, so one
+    buffer per stream is race-free; nothing is allocated on the steady-state path (CUDA-graph friendly)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def launch_count() -> int:
+    return int(load().apx_launch_count())
+
+
+# ---- thin functional wrappers (used by the processors, the encoder and the tests) ----------------------
+def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+           out_dtype: torch.dtype | None = None, gelu: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (apx_linear)."""
+    lib = load()
+    dev = require_cuda(a, w, bias, residual, out)
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.dtype == w.dtype
+    a = a if a.stride(1) == 1 else a.contiguous()
+    w = w if w.stride(1) == 1 else w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=dev)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+    with torch.cuda.device(dev):
+        check(lib.apx_linear(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(residual),
+                             residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
+                             dtype_code(a.dtype), dtype_code(out.dtype), APX_EPI_GELU if gelu else APX_EPI_NONE,
+                             stream_ptr()), "apx_linear")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, l0: int | None = None,
+              w0: float = 1.0, w1: float = 0.0) -> torch.Tensor:
+    """Segmented SDPA on token-major (B, S, H*d) / (B, L, H*d) views (apx_attention)."""
+    lib = load()
+    dev = require_cuda(q, k, v)
+    b, s, c = q.shape
+    l = k.shape[1]
+    l0 = l if l0 is None else l0
+    for t in (q, k, v):
+        assert t.stride(2) == 1 and t.dtype == q.dtype
+    o = torch.empty((b, s, c), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.apx_attention(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0),
+                                v.stride(1), ptr(o), o.stride(0), o.stride(1), b, s, heads, c // heads, l, l0, w0, w1,
+                                dtype_code(q.dtype), stream_ptr()), "apx_attention")
+    return o
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:
+    lib = load()
+    dev = require_cuda(x, w, b)
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == torch.float32 and b.dtype == torch.float32
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.apx_layernorm(ptr(x), ptr(w), ptr(b), ptr(y), rows, cols, eps, dtype_code(out_dtype), stream_ptr()),
+              "apx_layernorm")
+    return y

@@ -1,0 +1,238 @@
+"""Drop-in attention processors backed by the sm_100a kernels.
+
+Mirrors the reference interface (``APadapter/ap_adapter/attention_processor.py``): same class names, constructor
+arguments, attribute names (``to_k_ip``, ``to_v_ip``, ``scale``, ``num_tokens``, ``name`` ...), ``__call__``
+signature and checkpoint formats, so ``inference.py:22-59`` / ``train_apadapter_v2.py:613-669`` can build and
+register them unchanged with ``unet.set_attn_processor``.
+
+Differences that are deliberate (SURVEY.md §8 a-2'):
+* ``scale != 1.0`` passed to ``__call__`` warns instead of hitting the reference's undefined ``logger`` (NameError,
+  attention_processor.py:356-357).
+* a non-None ``attention_mask`` on the adapter site raises: the pipeline never passes one for the 768-d context
+  (pipeline_audioldm2.py:1010-1017) and the reference's ``split`` hack (:424-428) is not reproduced.
+* the context K/V projections (attention_processor.py:406-407,435-436) are timestep-invariant; they are computed
+  once per (context, weights) and cached on the processor instead of being recomputed every denoise step.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _copied_weight_dir() -> str:
+    """``../copied_cross_attention`` relative to the package, as the reference resolves it
+    (attention_processor.py:330-335); overridable for deployments that keep the files elsewhere."""
+    return os.environ.get(
+        "APX_COPIED_CROSS_ATTENTION",
+        os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "copied_cross_attention"))
+
+
+class AttnProcessor2_0(nn.Module):
+    """Plain scaled-dot-product attention processor for the non-adapter sites (self-attention, T5 cross-attention).
+
+    Reference: attention_processor.py:199-294.  These 224 sites are outside the adapter hot path
+    and stay a thin PyTorch module: cuBLAS projections + torch SDPA, with the reference's mask handling.
+    """
+
+    def __init__(self, hidden_size=None, cross_attention_dim=None):
+        super().__init__()
+        if not hasattr(F, "scaled_dot_product_attention"):
+            raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        residual = hidden_states
+        if attn.spatial_norm is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            batch_size, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+        if encoder_hidden_states is not None and encoder_hidden_states.dim() < 3:
+            encoder_hidden_states = encoder_hidden_states.unsqueeze(0)
+        batch_size, sequence_length, _ = (
+            hidden_states.shape if encoder_hidden_states is None else encoder_hidden_states.shape)
+        if attention_mask is not None:
+            attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+            attention_mask = attention_mask.view(batch_size, attn.heads, -1, attention_mask.shape[-1])
+        if attn.group_norm is not None:
+            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif attn.norm_cross:
+            encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        head_dim = key.shape[-1] // attn.heads
+        query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
+                                                       is_causal=False)
+        hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+        if attn.residual_connection:
+            hidden_states = hidden_states + residual
+        return hidden_states / attn.rescale_output_factor
+
+
+class IPAttnProcessor2_0(nn.Module):
+    r"""Decoupled (text + ``scale`` · audio) cross-attention processor on the B200 kernels.
+
+    Reference: ``IPAttnProcessor2_0`` (attention_processor.py:297-470).  Same constructor:
+
+    Args:
+        hidden_size (`int`): hidden size of the attention layer (C).
+        name (`str`): processor key, e.g. ``down_blocks.1.attentions.1.transformer_blocks.0.attn2.processor``.
+        cross_attention_dim (`int`): channels of ``encoder_hidden_states`` (768).
+        num_tokens (`int`, defaults to 4): number of leading TEXT tokens in the context; the rest is audio
+            (attention_processor.py:400-403).
+        scale (`float`, defaults to 1.0): ``ap_scale``, weight of the audio branch.
+        do_copy (`bool`): initialise ``to_k_ip`` / ``to_v_ip`` from ``copied_cross_attention/<name>_{k,v}.bin``.
+    """
+
+    def __init__(self, hidden_size, name, cross_attention_dim=None, num_tokens=4, scale=1.0, do_copy=False):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.cross_attention_dim = cross_attention_dim
+        self.num_tokens = num_tokens
+        self.scale = scale
+        self.to_k_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+        self.to_v_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+        self.name = name
+        self._ctx_cache = None  # (key, cache blob, keyed tensors)
+        if do_copy:
+            from .weights import load_copied_cross_attention
+            k_weight, v_weight = load_copied_cross_attention(_copied_weight_dir(), name)
+            self.to_k_ip.weight = nn.Parameter(k_weight.to(torch.float32))
+            self.to_v_ip.weight = nn.Parameter(v_weight.to(torch.float32))
+            self.to_k_ip.weight.requires_grad = True
+            self.to_v_ip.weight.requires_grad = True
+
+    # -- context K/V cache -------------------------------------------------------------------------------
+    @staticmethod
+    def _tkey(t: torch.Tensor):
+        return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+    def invalidate_cache(self):
+        self._ctx_cache = None
+
+    def _context_cache(self, attn, ctx: torch.Tensor, heads: int, dtype: torch.dtype) -> torch.Tensor:
+        wk, wv = attn.to_k.weight, attn.to_v.weight
+        wk_ip, wv_ip = self.to_k_ip.weight, self.to_v_ip.weight
+        key = (self._tkey(ctx), self._tkey(wk), self._tkey(wv), self._tkey(wk_ip), self._tkey(wv_ip), heads, self.num_tokens)
+        if self._ctx_cache is not None and self._ctx_cache[0] == key:
+            return self._ctx_cache[1]
+        lib = _lib.load()
+        bc, l, dctx = ctx.shape
+        lt = min(self.num_tokens, l)
+        la = l - lt
+        c = self.hidden_size
+        ws = [w.detach().to(dtype).contiguous() for w in (wk, wv, wk_ip, wv_ip)]
+        for w in ws:
+            if tuple(w.shape) != (c, dctx):
+                raise _lib.ApxError(f"{self.name}: K/V projection weight {tuple(w.shape)} != ({c}, {dctx})")
+        ctx_c = ctx.detach().to(dtype).contiguous()
+        nbytes = lib.apx_ctx_kv_bytes(bc, lt, la, c, heads)
+        cache = torch.empty(nbytes, dtype=torch.uint8, device=ctx.device)
+        wsb = lib.apx_ctx_kv_workspace_bytes(bc, lt, la, c)
+        work = _lib.workspace(wsb, ctx.device, "ctx_kv")
+        with torch.cuda.device(ctx.device):
+            _lib.check(lib.apx_ctx_kv(_lib.ptr(ctx_c), *[_lib.ptr(w) for w in ws], _lib.ptr(cache), bc, lt, la, dctx, c, heads,
+                                      _lib.dtype_code(dtype), _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_ctx_kv")
+        # the keyed tensors are kept alive with the entry so that their addresses cannot be recycled under the key
+        self._ctx_cache = (key, cache, (ctx, wk, wv, wk_ip, wv_ip))
+        return cache
+
+    # -- forward -----------------------------------------------------------------------------------------
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+        if scale != 1.0:
+            warnings.warn("`scale` of IPAttnProcessor should be set by `set_ip_adapter_scale`.")
+        if attention_mask is not None:
+            raise NotImplementedError(
+                "IPAttnProcessor2_0: attention_mask on the adapter site is not implemented (the AP-adapter pipeline never "
+                "passes one for the 768-d context; reference attention_processor.py:378-382,424-428 is a dead path)")
+        _lib.require_cuda(hidden_states, encoder_hidden_states)
+        if torch.is_grad_enabled() and (hidden_states.requires_grad or self.to_k_ip.weight.requires_grad
+                                        or self.to_v_ip.weight.requires_grad):
+            raise NotImplementedError(
+                "IPAttnProcessor2_0: the sm_100a path is forward-only in this release; call it under torch.no_grad() "
+                "(adapter training backward is the next scope row, SURVEY.md §8f-1)")
+        residual = hidden_states
+        if attn.spatial_norm is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            batch_size, channel, height, width = hidden_states.shape
+            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+        if encoder_hidden_states is None:
+            # reference :389-390 would attend to the hidden states themselves; with to_k_ip built for the
+            # cross-attention width this only type-checks when cross_attention_dim == hidden_size.
+            encoder_hidden_states = hidden_states
+        elif encoder_hidden_states.dim() < 3:
+            encoder_hidden_states = encoder_hidden_states.unsqueeze(0)
+        if attn.group_norm is not None:
+            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+        if attn.norm_cross:
+            encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
+
+        dtype = hidden_states.dtype
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise _lib.ApxError(f"IPAttnProcessor2_0: hidden_states dtype {dtype}; the kernels take float16 / bfloat16 "
+                                "(the reference runs inference in fp16, inference.py:13)")
+        batch_size = encoder_hidden_states.shape[0]  # reference :374-376
+        x = hidden_states.contiguous()
+        if x.shape[0] != batch_size:
+            raise _lib.ApxError(f"{self.name}: hidden_states batch {x.shape[0]} != context batch {batch_size}")
+        bc, s, c = x.shape
+        if c != self.hidden_size:
+            raise _lib.ApxError(f"{self.name}: hidden size {c} != {self.hidden_size}")
+        heads = attn.heads
+        lt = min(self.num_tokens, encoder_hidden_states.shape[1])
+        la = encoder_hidden_states.shape[1] - lt
+
+        lib = _lib.load()
+        cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
+        wq = attn.to_q.weight.detach()
+        wo = attn.to_out[0].weight.detach()
+        if getattr(attn.to_q, "bias", None) is not None:
+            raise _lib.ApxError(f"{self.name}: to_q with bias is not implemented (attention_bias=False in AudioLDM2)")
+        wq = wq if wq.dtype == dtype and wq.is_contiguous() else wq.to(dtype).contiguous()
+        wo = wo if wo.dtype == dtype and wo.is_contiguous() else wo.to(dtype).contiguous()
+        bo = attn.to_out[0].bias
+        if bo is not None:
+            bo = self._bias_f32(bo)
+        y = torch.empty_like(x)
+        wsb = lib.apx_ipattn_workspace_bytes(bc, s, c)
+        work = _lib.workspace(wsb, x.device, "ipattn")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(bo), _lib.ptr(y),
+                                          bc, s, c, heads, lt, la, float(self.scale), _lib.dtype_code(dtype), _lib.ptr(work),
+                                          wsb, _lib.stream_ptr()), "apx_ipattn_fwd")
+        hidden_states = attn.to_out[1](y)  # dropout (p = 0)
+        if input_ndim == 4:
+            hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+        if attn.residual_connection:
+            hidden_states = hidden_states + residual
+        if attn.rescale_output_factor != 1.0:
+            hidden_states = hidden_states / attn.rescale_output_factor
+        return hidden_states
+
+    def _bias_f32(self, bo: torch.Tensor) -> torch.Tensor:
+        """fp32 copy of the out-projection bias (the epilogue adds it to the fp32 accumulator), cached per version."""
+        key = self._tkey(bo)
+        cached = getattr(self, "_bo_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, bo.detach().float().contiguous(), bo)
+            self._bo_cache = cached
+        return cached[1]

@@ -257,24 +257,14 @@ static MaeWorkspace mae_ws(int B) {
 }
 size_t apx_audiomae_workspace_bytes(int B) { return B > 0 ? mae_ws(B).total : 0; }
 
-int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w, float* emb, int B, int time_pool, int freq_pool,
-                     void* workspace, size_t workspace_bytes, void* stream) {
-    APX_REQUIRE(mel && w && emb && workspace && w->blocks, APX_EINVAL, "apx_audiomae_fwd: null pointer");
-    APX_REQUIRE(B > 0, APX_EINVAL, "apx_audiomae_fwd: B=%d", B);
-    APX_REQUIRE(w->embed == 768 && w->heads == 12 && w->mlp == 3072 && w->depth > 0, APX_EUNSUPPORTED,
-                "apx_audiomae_fwd: only the ViT-B geometry (768/12/3072) is implemented, got %d/%d/%d", w->embed,
-                w->heads, w->mlp);
-    APX_REQUIRE(w->wdtype == APX_F16 || w->wdtype == APX_BF16, APX_EUNSUPPORTED, "apx_audiomae_fwd: wdtype %d", w->wdtype);
-    const MaeWorkspace ws = mae_ws(B);
-    APX_REQUIRE(workspace_bytes >= ws.total, APX_EWORKSPACE, "apx_audiomae_fwd: workspace %zu < %zu", workspace_bytes,
-                ws.total);
-    uint8_t* base = static_cast<uint8_t*>(workspace);
+// patch-embed -> depth x (LN, QKV, attention, proj+res, LN, fc1+GELU, fc2+res) -> final LN into `tokens`
+static int audiomae_encode_into(const float* mel, const apx_vit_weights* w, float* tokens, int B, uint8_t* base,
+                                const MaeWorkspace& ws, void* stream) {
     float* x = reinterpret_cast<float*>(base + ws.x);
     void* xn = base + ws.xn;
     uint16_t* qkv = reinterpret_cast<uint16_t*>(base + ws.qkv);
     void* att = base + ws.att;
     void* hid = base + ws.hid;
-    float* xf = reinterpret_cast<float*>(base + ws.xf);
     const int rows = B * 513, dt = w->wdtype;
     const float eps = 1e-6f;  // partial(nn.LayerNorm, eps=1e-6): audio_encoder/models_mae.py:698
     int rc;
@@ -293,10 +283,41 @@ int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w, float* emb, int
         APX_STEP(apx_linear(xn, 768, k.fc1_w, 768, k.fc1_b, nullptr, 0, hid, 3072, rows, 3072, 768, dt, dt, APX_EPI_GELU, stream));
         APX_STEP(apx_linear(hid, 3072, k.fc2_w, 3072, k.fc2_b, x, 768, x, 768, rows, 768, 3072, dt, APX_F32, APX_EPI_NONE, stream));
     }
-    APX_STEP(apx_layernorm(x, w->norm_w, w->norm_b, xf, rows, 768, eps, APX_F32, stream));
-    APX_STEP(apx_pool_tokens(xf, emb, B, time_pool, freq_pool, stream));
+    APX_STEP(apx_layernorm(x, w->norm_w, w->norm_b, tokens, rows, 768, eps, APX_F32, stream));
 #undef APX_STEP
     return APX_OK;
+}
+
+static int audiomae_check(const float* mel, const apx_vit_weights* w, const void* out, int B, const void* workspace,
+                          size_t workspace_bytes) {
+    APX_REQUIRE(mel && w && out && workspace && w->blocks, APX_EINVAL, "apx_audiomae: null pointer");
+    APX_REQUIRE(B > 0, APX_EINVAL, "apx_audiomae: B=%d", B);
+    APX_REQUIRE(w->embed == 768 && w->heads == 12 && w->mlp == 3072 && w->depth > 0, APX_EUNSUPPORTED,
+                "apx_audiomae: only the ViT-B geometry (768/12/3072) is implemented, got %d/%d/%d", w->embed, w->heads,
+                w->mlp);
+    APX_REQUIRE(w->wdtype == APX_F16 || w->wdtype == APX_BF16, APX_EUNSUPPORTED, "apx_audiomae: wdtype %d", w->wdtype);
+    APX_REQUIRE(workspace_bytes >= mae_ws(B).total, APX_EWORKSPACE, "apx_audiomae: workspace %zu < %zu", workspace_bytes,
+                mae_ws(B).total);
+    return APX_OK;
+}
+
+int apx_audiomae_encode(const float* mel, const apx_vit_weights* w, float* tokens, int B, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    int rc = audiomae_check(mel, w, tokens, B, workspace, workspace_bytes);
+    if (rc) return rc;
+    return audiomae_encode_into(mel, w, tokens, B, static_cast<uint8_t*>(workspace), mae_ws(B), stream);
+}
+
+int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w, float* emb, int B, int time_pool, int freq_pool,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = audiomae_check(mel, w, emb, B, workspace, workspace_bytes);
+    if (rc) return rc;
+    const MaeWorkspace ws = mae_ws(B);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float* xf = reinterpret_cast<float*>(base + ws.xf);
+    rc = audiomae_encode_into(mel, w, xf, B, base, ws, stream);
+    if (rc) return rc;
+    return apx_pool_tokens(xf, emb, B, time_pool, freq_pool, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,227 @@
+"""The caller of the hot path: audio-conditioning block + classifier-free-guidance DDIM loop.
+
+Restates the part of ``AudioLDM2Pipeline.__call__`` that touches the adapter (reference
+``pipeline/pipeline_audioldm2.py``): the AudioMAE conditioning block (:919-956), latent preparation (:983-996) and
+the denoising loop with CFG (:1001-1031).  Text encoders (CLAP / T5 / GPT-2), VAE and vocoder are frozen HF models
+with no weights offline and are out of scope: their outputs (``prompt_embeds``,
+``attention_mask``, ``generated_prompt_embeds``) are inputs here.
+
+B200-first differences from the reference loop, all output-identical:
+* the AudioMAE model is built once and kept (the reference re-instantiates it and re-reads the checkpoint on every
+  call, :926); the zero-mel unconditional embedding is cached per pooling;
+* the context K/V of all 32 adapter sites are computed once per generation (they do not depend on the timestep);
+* one denoise step (cat -> UNet -> CFG -> DDIM update) is captured in a CUDA graph and replayed, with the timestep
+  and the DDIM coefficients read from device memory, so the 200-step loop has no per-step host work;
+* clips shard across ranks (one process per GPU); the only collective is the final gather of latents.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+class DDIMScheduler:
+    """HF ``DDIMScheduler`` (eta = 0, epsilon prediction), restated from SURVEY.md appendix A.  The β schedule of
+    ``cvssp/audioldm2-large`` lives in the hub config, which is unreachable offline: ``scaled_linear`` 0.0015 -> 0.0195
+    over 1000 train steps, ``steps_offset=1``, ``set_alpha_to_one=False`` are used as SYNTHETIC defaults."""
+
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0015, beta_end: float = 0.0195,
+                 steps_offset: int = 1, set_alpha_to_one: bool = False, prediction_type: str = "epsilon"):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_train_timesteps = num_train_timesteps
+        self.steps_offset = steps_offset
+        self.prediction_type = prediction_type
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
+        self.num_inference_steps = None
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        if num_inference_steps > self.num_train_timesteps:
+            raise ValueError(f"num_inference_steps {num_inference_steps} > {self.num_train_timesteps}")
+        self.num_inference_steps = num_inference_steps
+        ratio = self.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.steps_offset
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def coefficients(self, device=None):
+        """Per-step (sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)) as a (steps, 4) fp32 table."""
+        ts = self.timesteps.cpu()
+        prev = ts - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[ts]
+        a_p = torch.where(prev >= 0, self.alphas_cumprod[prev.clamp(min=0)], self.final_alpha_cumprod)
+        return torch.stack([a_t.sqrt(), (1 - a_t).sqrt(), a_p.sqrt(), (1 - a_p).sqrt()], dim=1).to(device)
+
+    @staticmethod
+    def step_with(coef, model_output, sample, prediction_type: str = "epsilon"):
+        """x_{t-1} from (eps | v) and x_t with the 4 coefficients of this step (device tensor, no host sync)."""
+        sa, s1a, sp, s1p = coef[0], coef[1], coef[2], coef[3]
+        mo, x = model_output.float(), sample.float()
+        if prediction_type == "epsilon":
+            x0 = (x - s1a * mo) / sa
+            eps = mo
+        elif prediction_type == "v_prediction":
+            x0 = sa * x - s1a * mo
+            eps = sa * mo + s1a * x
+        else:
+            raise ValueError(prediction_type)
+        return (sp * x0 + s1p * eps).to(sample.dtype)
+
+    def step(self, model_output, timestep, sample):
+        idx = int((self.timesteps == int(timestep)).nonzero()[0])
+        coef = self.coefficients(sample.device)[idx]
+        return DDIMScheduler.step_with(coef, model_output, sample, self.prediction_type)
+
+
+class APAdapterDenoiser(nn.Module):
+    """AudioMAE conditioning + CFG/DDIM denoising around a UNet whose ``attn2`` sites carry the adapter processors."""
+
+    def __init__(self, unet: nn.Module, audiomae: Optional[nn.Module] = None, scheduler: Optional[DDIMScheduler] = None,
+                 vae_scale_factor: int = 4):
+        super().__init__()
+        self.unet = unet
+        self.audiomae = audiomae
+        self.scheduler = scheduler or DDIMScheduler()
+        self.vae_scale_factor = vae_scale_factor
+        self._uncond_cache = {}
+        self._graph = None
+
+    # ---- pipeline_audioldm2.py:919-956 ------------------------------------------------------------------------
+    @torch.no_grad()
+    def audio_condition(self, mel: torch.Tensor, generated_prompt_embeds: torch.Tensor, time_pooling: int,
+                        freq_pooling: int) -> torch.Tensor:
+        """mel (1,1024,128) [or (n,1024,128)]; generated_prompt_embeds (2B, Lt, 768) = cat([negative, positive]).
+        Returns (2B, Lt + La, 768): rows [0,B) = cat([neg_g, AudioMAE(zeros)]), rows [B,2B) = cat([g, AudioMAE(mel)])."""
+        if self.audiomae is None:
+            raise RuntimeError("APAdapterDenoiser was built without an AudioMAE encoder")
+        loa = self.audiomae(mel, time_pool=time_pooling, freq_pool=freq_pooling)[0]
+        key = (time_pooling, freq_pooling, tuple(mel.shape), loa.dtype)
+        if key not in self._uncond_cache:  # AudioMAE(zeros) is a constant of the weights and the pooling
+            self._uncond_cache[key] = self.audiomae(torch.zeros_like(mel), time_pool=time_pooling, freq_pool=freq_pooling)[0]
+        uncond_loa = self._uncond_cache[key]
+        num = generated_prompt_embeds.shape[0] // 2
+        loa = loa.repeat(num, 1, 1)
+        uncond_loa = uncond_loa.repeat(num, 1, 1)
+        negative_g, g = generated_prompt_embeds.chunk(2)
+        uncond = torch.cat([negative_g, uncond_loa.to(negative_g.dtype)], dim=1)
+        cond = torch.cat([g, loa.to(g.dtype)], dim=1)
+        model_dtype = next(self.unet.parameters()).dtype
+        return torch.cat([uncond, cond], dim=0).to(model_dtype).contiguous()
+
+    def prepare_latents(self, batch_size: int, height: int, dtype, device, generator=None, latents=None):
+        """pipeline_audioldm2.py:724-746: (B, C_lat, height / vae_scale, n_mel(64) / vae_scale) * init_noise_sigma."""
+        shape = (batch_size, self.unet.config.in_channels, height // self.vae_scale_factor, 64 // self.vae_scale_factor)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        else:
+            latents = latents.to(device=device, dtype=dtype)
+        return latents * self.scheduler.init_noise_sigma
+
+    # ---- one denoise step (pipeline_audioldm2.py:1004-1025) -------------------------------------------------------
+    def denoise_step(self, latents, t, coef, generated_prompt_embeds, prompt_embeds, attention_mask, guidance_scale):
+        x = torch.cat([latents] * 2) if guidance_scale > 1.0 else latents
+        noise = self.unet(x, t, encoder_hidden_states=generated_prompt_embeds, encoder_hidden_states_1=prompt_embeds,
+                          encoder_attention_mask_1=attention_mask, return_dict=False)[0]
+        if guidance_scale > 1.0:
+            n_u, n_t = noise.chunk(2)
+            noise = n_u + guidance_scale * (n_t - n_u)
+        return DDIMScheduler.step_with(coef, noise, latents, self.scheduler.prediction_type)
+
+    @torch.no_grad()
+    def denoise(self, latents, generated_prompt_embeds, prompt_embeds, attention_mask, num_inference_steps: int = 200,
+                guidance_scale: float = 3.5, use_cuda_graph: bool = True, steps_to_run: Optional[int] = None):
+        """The DDIM loop.  ``steps_to_run`` < num_inference_steps runs a prefix of the schedule (benchmarks)."""
+        dev = latents.device
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        ts = self.scheduler.timesteps
+        coefs = self.scheduler.coefficients(dev)
+        n = len(ts) if steps_to_run is None else min(steps_to_run, len(ts))
+        if not (use_cuda_graph and latents.is_cuda):
+            for i in range(n):
+                latents = self.denoise_step(latents, ts[i], coefs[i], generated_prompt_embeds, prompt_embeds,
+                                            attention_mask, guidance_scale)
+            return latents
+        g = self._step_graph(latents, generated_prompt_embeds, prompt_embeds, attention_mask, guidance_scale)
+        g["latents"].copy_(latents)
+        for i in range(n):
+            g["t"].copy_(ts[i])        # device -> device, stream-ordered: no host synchronisation in the loop
+            g["coef"].copy_(coefs[i])
+            g["graph"].replay()
+            g["latents"].copy_(g["out"])
+        return g["latents"].clone()
+
+    def _step_graph(self, latents, gpe, pe, mask, guidance_scale):
+        key = (tuple(latents.shape), latents.dtype, gpe.data_ptr(), gpe._version, pe.data_ptr(), pe._version,
+               None if mask is None else mask.data_ptr(), float(guidance_scale))
+        if self._graph is not None and self._graph["key"] == key:
+            return self._graph
+        dev = latents.device
+        st = dict(key=key, latents=torch.zeros_like(latents), t=torch.zeros((), dtype=torch.int64, device=dev),
+                  coef=torch.ones(4, dtype=torch.float32, device=dev), keep=(gpe, pe, mask))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up off the capture: builds the context-KV caches, cuDNN plans, workspaces
+            for _ in range(2):
+                self.denoise_step(st["latents"], st["t"], st["coef"], gpe, pe, mask, guidance_scale)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["out"] = self.denoise_step(st["latents"], st["t"], st["coef"], gpe, pe, mask, guidance_scale)
+        st["graph"] = graph
+        self._graph = st
+        return st
+
+    # ---- end to end (pipeline_audioldm2.py:748-1034, minus text encoders / VAE / vocoder) -------------------------------
+    @torch.no_grad()
+    def __call__(self, mel, prompt_embeds, attention_mask, generated_prompt_embeds, time_pooling: int = 2,
+                 freq_pooling: int = 2, num_inference_steps: int = 200, guidance_scale: float = 3.5,
+                 audio_length_in_s: float = 10.0, generator=None, latents=None, use_cuda_graph: bool = True):
+        """``prompt_embeds`` (2B, L_T5, 1024), ``attention_mask`` (2B, L_T5), ``generated_prompt_embeds`` (2B, 8, 768):
+        the [negative; positive] outputs of ``encode_prompt`` (:902-915).  Returns the final latents (B, 8, T/4, 16)."""
+        gpe = self.audio_condition(mel, generated_prompt_embeds, time_pooling, freq_pooling)
+        batch = gpe.shape[0] // 2
+        height = int(audio_length_in_s / 0.01)  # :861 vocoder_upsample_factor = hop / sr = 160 / 16000
+        if height % self.vae_scale_factor != 0:
+            height = int(np.ceil(height / self.vae_scale_factor)) * self.vae_scale_factor
+        latents = self.prepare_latents(batch, height, gpe.dtype, gpe.device, generator, latents)
+        return self.denoise(latents, gpe, prompt_embeds.to(gpe.dtype), attention_mask, num_inference_steps,
+                            guidance_scale, use_cuda_graph)
+
+
+# ---- batch sharding across ranks -------------------------------------------------------------------
+def shard_range(n_items: int, rank: int, world_size: int):
+    """Contiguous shard [lo, hi) of ``n_items`` clips for ``rank``; the first ``n_items % world_size`` ranks take one more."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_latents(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """All-gather per-rank latents (shards from ``shard_range``) into the full (n_items, ...) tensor on every rank.
+    The only collective of batch-sharded inference: 64 KB per clip in fp16."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    per = -(-n_items // world)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_items, r, world)
+        parts.append(out[r * per: r * per + (hi - lo)])
+    del rank
+    return torch.cat(parts, dim=0)

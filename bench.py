@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — UNet denoise steps/s (10 s clip, 200-step DDIM schedule) with the AP-adapter hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one denoise step of BASELINE.json configs[1]: CFG concat -> AudioLDM2-large UNet (random init, the geometry
+the shipped adapter weights imply, fp16) with the 32 adapter sites running in libapx.so -> guidance -> DDIM update, for
+B clips per GPU (default 1) of 10 s (latent 8x250x16), text context 8 tokens + 128 AudioMAE tokens (timbre_transfer
+preset: time/freq pooling 2), T5 context 16 tokens.  Ranks run independent clips (weak scaling); the only collective
+is the final gather of latents.
+
+Prints ONE JSON line (rank 0).  `value` is timed on the device with inputs resident in HBM; `e2e` runs the same steps
+through the public API with the step's latents coming from / going back to pinned host memory every step.
+`--impl reference` times the reference algorithm (oracle port: same UNet, fp32, reference-semantics processors) on the
+host CPUs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "unet_denoise_steps_per_s"
+UNIT = "steps/s"
+LT, LA, L_T5 = 8, 128, 16
+LAT_SHAPE = (8, 250, 16)
+INFER_STEPS = 200
+GUIDANCE = 7.5
+AP_SCALE = 0.5
+
+
+def workload_config(batch: int, n_gpus: int) -> dict:
+    return {"workload": "BASELINE configs[1]: AudioLDM2-large UNet single denoise step (CFG, DDIM-200 schedule) with AP "
+                        "attn2 processors at 32 sites, 10 s latent (8x250x16)",
+            "clips_per_gpu": batch, "cfg_batch_per_gpu": 2 * batch, "text_tokens": LT, "audio_tokens": LA,
+            "t5_tokens": L_T5, "ap_scale": AP_SCALE, "guidance_scale": GUIDANCE, "ddim_steps": INFER_STEPS,
+            "parallelism": f"clips sharded over {n_gpus} rank(s), no data-path collective, final all-gather of latents",
+            "l2": "per-step working set (1.4 GB of fp16 UNet weights) exceeds the 126 MB L2; no flush needed"}
+
+
+def peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
+    """The reference algorithm on the host CPUs: restated UNet in fp32 with the oracle port of IPAttnProcessor2_0 /
+    AttnProcessor2_0 at every site (the reference itself is pure Python on diffusers, which this image lacks)."""
+    from ap_adapter_b200.pipeline import APAdapterDenoiser
+    from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+    from oracle.ref_processors import OracleAttnProcessor2_0, OracleIPAttnProcessor2_0
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval()
+    unet.set_attn_processor(build_attn_processors(unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=AP_SCALE))
+    den = APAdapterDenoiser(unet)
+    g = torch.Generator().manual_seed(1)
+    lat = torch.randn(batch, *LAT_SHAPE, generator=g)
+    gpe = torch.randn(2 * batch, LT + LA, 768, generator=g)
+    pe = torch.randn(2 * batch, L_T5, 1024, generator=g)
+    mask = torch.ones(2 * batch, L_T5)
+    den.scheduler.set_timesteps(INFER_STEPS)
+    ts, coefs = den.scheduler.timesteps, den.scheduler.coefficients()
+    times = []
+    with torch.no_grad():
+        i = 0
+        for _ in range(max(1, warmup)):
+            t0 = time.perf_counter()
+            lat = den.denoise_step(lat, ts[i % INFER_STEPS], coefs[i % INFER_STEPS], gpe, pe, mask, GUIDANCE)
+            est = time.perf_counter() - t0
+            i += 1
+            if est * (warmup + steps) > budget_s:
+                break  # slow host: one warm-up step is all the budget allows
+        n = max(1, min(steps, int(budget_s / max(est, 1e-3))))
+        for _ in range(n):
+            t0 = time.perf_counter()
+            lat = den.denoise_step(lat, ts[i % INFER_STEPS], coefs[i % INFER_STEPS], gpe, pe, mask, GUIDANCE)
+            times.append(time.perf_counter() - t0)
+            i += 1
+    assert torch.isfinite(lat).all()
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} full fp32 UNet denoise steps of the same workload (B={batch}) after {i - len(times)} warm-up, "
+                      f"torch {torch.__version__} with {torch.get_num_threads()} threads",
+            "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times)}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:
+            ident = str(device_index)
+        self.cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", ident]
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def site_roofline(batch: int, iters: int = 30) -> dict:
+    """The dominant kernel of the hot path: the adapter site at the S=1000, C=256 geometry (10 of the 32 sites, and the
+    one that moves the most bytes).  Timed through apx_ipattn_fwd on the current stream with CUDA events, rotating over
+    enough distinct copies of every operand (X, Y, Wq, Wo, context cache, workspace) that no launch finds its inputs
+    in the 126 MB L2."""
+    from ap_adapter_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bc, s, c, h, d = 2 * batch, 1000, 256, 8, 768
+    per_copy = 4 * bc * s * c * 2 + 2 * c * c * 2
+    r = max(4, min(256, int(2.5 * 126e6 / per_copy) + 1))
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(r, bc, s, c, generator=g, device=dev, dtype=torch.float16)
+    y = torch.empty_like(x)
+    wq = torch.randn(r, c, c, generator=g, device=dev, dtype=torch.float16) * c ** -0.5
+    wo = torch.randn(r, c, c, generator=g, device=dev, dtype=torch.float16) * c ** -0.5
+    bo = torch.zeros(c, device=dev)
+    ctx = torch.randn(bc, LT + LA, d, generator=g, device=dev, dtype=torch.float16)
+    wkv = [torch.randn(c, d, generator=g, device=dev, dtype=torch.float16) * d ** -0.5 for _ in range(4)]
+    cbytes = lib.apx_ctx_kv_bytes(bc, LT, LA, c, h)
+    cache = torch.empty(r, (cbytes + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    wsb = max(lib.apx_ctx_kv_workspace_bytes(bc, LT, LA, c), lib.apx_ipattn_workspace_bytes(bc, s, c))
+    ws = torch.empty(r, (wsb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
+    st = _lib.stream_ptr()
+    for i in range(r):
+        _lib.check(lib.apx_ctx_kv(_lib.ptr(ctx), *[_lib.ptr(w) for w in wkv], _lib.ptr(cache[i]), bc, LT, LA, d, c, h, 0,
+                                  _lib.ptr(ws[i]), wsb, st), "apx_ctx_kv")
+
+    def launch(i):
+        _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x[i]), _lib.ptr(wq[i]), _lib.ptr(cache[i]), _lib.ptr(wo[i]), _lib.ptr(bo),
+                                      _lib.ptr(y[i]), bc, s, c, h, LT, LA, AP_SCALE, 0, _lib.ptr(ws[i]), wsb, st), "apx_ipattn_fwd")
+
+    for i in range(r):
+        launch(i)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    n = iters * r
+    for k in range(n):
+        launch(k % r)
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / n
+    launches_per_call = (_lib.launch_count() - n0) // n
+    l_tot = LT + LA
+    flops = 4.0 * bc * s * c * c + 4.0 * bc * s * l_tot * c                # q-proj + out-proj + QK^T + PV
+    l_pad = (LT + 15) // 16 * 16 + (LA + 15) // 16 * 16
+    kv_bytes = 2 * bc * h * l_pad * (c // h) * 2                             # packed K + V^T tiles as read
+    byts = 2 * bc * s * c * 2 + 2 * c * c * 2 + kv_bytes + 4 * c           # X in, Y out, Wq, Wo, K/V cache, bias
+    pk = peaks()
+    t_tensor, t_hbm = flops / (pk["tflops"] * 1e12), byts / (pk["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_tensor >= t_hbm else "hbm"
+    if bound == "tensor":
+        achieved, peak, unit = flops / (us * 1e-6) / 1e12, pk["tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = byts / (us * 1e-6) / 1e9, pk["hbm_gbs"], "GB/s"
+    return {"kernel": f"adapter site via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
+            "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
+            "traffic": None, "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
+            "floor_us": round(1e6 * max(t_tensor, t_hbm), 3), "peak_source": pk["source"], "operand_copies_rotated": r}
+
+
+def run_ours(args) -> dict:
+    import torch.distributed as dist
+
+    from ap_adapter_b200 import _lib
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from ap_adapter_b200.pipeline import APAdapterDenoiser, gather_latents
+    from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: ap_adapter_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    assert lib.apx_device_ok() == 1, lib.apx_last_error().decode()
+
+    b = args.batch
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval().half().to(dev)
+    unet.set_attn_processor(build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device=dev, dtype=torch.float16))
+    den = APAdapterDenoiser(unet)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    lat0 = torch.randn(b, *LAT_SHAPE, generator=g, device=dev, dtype=torch.float16)
+    gpe = torch.randn(2 * b, LT + LA, 768, generator=g, device=dev, dtype=torch.float16)
+    pe = torch.randn(2 * b, L_T5, 1024, generator=g, device=dev, dtype=torch.float16)
+    mask = torch.ones(2 * b, L_T5, device=dev)
+    den.scheduler.set_timesteps(INFER_STEPS, device=dev)
+    ts, coefs = den.scheduler.timesteps, den.scheduler.coefficients(dev)
+
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        graph = den._step_graph(lat0, gpe, pe, mask, GUIDANCE)  # 2 eager warm-up steps + 1 captured step
+        per_step_launches = (_lib.launch_count() - n0) // 3
+
+        def step(i):
+            graph["t"].copy_(ts[i % INFER_STEPS])
+            graph["coef"].copy_(coefs[i % INFER_STEPS])
+            graph["graph"].replay()
+            graph["latents"].copy_(graph["out"])
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident timing -----------------------------------------------------------------
+        graph["latents"].copy_(lat0)
+        for i in range(max(3, args.warmup)):
+            step(i)
+        graph["latents"].copy_(lat0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            w0 = time.perf_counter()
+            e0.record()
+            for i in range(args.steps):
+                step(i)
+            final = gather_latents(graph["latents"], world * b) if world > 1 else graph["latents"]
+            e1.record()
+            barrier()
+            w1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        assert torch.isfinite(final).all(), "non-finite latents"
+        clocks = clk.summary(w0, w1)
+
+        # ---- end to end: the step's latents come from and go back to pinned host memory every step ------------------
+        h_lat = lat0.cpu().pin_memory()
+        h_t = ts.cpu().pin_memory()
+        h_coef = coefs.cpu().pin_memory()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def e2e_step(i):
+            graph["latents"].copy_(h_lat, non_blocking=True)
+            graph["t"].copy_(h_t[i % INFER_STEPS], non_blocking=True)
+            graph["coef"].copy_(h_coef[i % INFER_STEPS], non_blocking=True)
+            graph["graph"].replay()
+            h_lat.copy_(graph["out"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads x_{t-1} before issuing the next step
+
+        for i in range(3):
+            e2e_step(i)
+        h_lat.copy_(lat0)
+        barrier()
+        e2.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+        assert torch.isfinite(h_lat).all()
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    lat_bytes = h_lat.numel() * h_lat.element_size()
+    out = {
+        "metric": METRIC, "value": world * b * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init UNet / adapter weights, N(0,1) latents and contexts)",
+        "config": workload_config(b, world), "impl": "ours",
+        "e2e": {"value": world * b * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": lat_bytes + 8 + 16,
+                "d2h_bytes_per_step": lat_bytes, "ms_per_step": ms_e2e / args.steps,
+                "path": "APAdapterDenoiser step graph: pinned-host latents/timestep/DDIM coefficients -> HBM, replay, x_{t-1} -> pinned host, sync"},
+        "gpu_launches": per_step_launches * args.steps, "gpu_launches_per_step": per_step_launches,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        out["roofline"] = site_roofline(b)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(b, steps=3, warmup=1, budget_s=25.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+def run_reference(args) -> dict:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return None
+    r = cpu_reference(args.batch, steps=args.steps, warmup=max(1, min(args.warmup, 2)), budget_s=150.0)
+    return {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"],
+            "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (random-init UNet / adapter weights, N(0,1) latents and contexts)",
+            "config": workload_config(args.batch, 1), "impl": "reference",
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="clips per GPU (CFG doubles it inside the UNet)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,11 @@ int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w_host, float* emb
                      int B, int time_pool, int freq_pool,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* same, stopping before the pooling: tokens fp32 [B, 513, 768] = final-LayerNorm output incl. the CLS row
+ * (audio_encoder/models_mae.py:548-570, forward_encoder_no_random_mask_no_average)                      */
+int apx_audiomae_encode(const float* mel, const apx_vit_weights* w_host, float* tokens, int B,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* individual stages (also used by the parity tests) */
 int apx_patch_embed(const float* mel, const float* patch_wT, const float* patch_b,
                     const float* pos_embed, const float* cls_token, float* x, int B, void* stream);

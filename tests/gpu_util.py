@@ -1,0 +1,47 @@
+"""Shared helpers of the GPU parity tests."""
+import torch
+
+from oracle import cases, ipattn_oracle, ref_shims
+
+# max|err| / max|ref| against the fp32 oracle fed with the SAME 16-bit-rounded operands.
+# north_star: "within 1e-3 relative (fp16/bf16)".  fp16 meets 1e-3.  bf16 stores 8 significand bits, so the output
+# rounding alone is 2^-9 = 2e-3 relative and the intermediate Q / P / O roundings add to it: 8e-3 is the bound there.
+TOL = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
+
+
+def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def rounded(t: torch.Tensor, dtype) -> torch.Tensor:
+    return t.to(dtype).float()
+
+
+def build_site(case: dict, dtype, device="cuda"):
+    """(attn stub, product processor) on the device for one oracle case dict."""
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+
+    hidden = case["wq"].shape[0]
+    attn = ref_shims.StubAttention(hidden, cases.DCTX, case["heads"])
+    proc = IPAttnProcessor2_0(hidden, "test", cases.DCTX, num_tokens=case["num_tokens"], scale=case["scale"])
+    with torch.no_grad():
+        attn.to_q.weight.copy_(case["wq"]); attn.to_k.weight.copy_(case["wk"]); attn.to_v.weight.copy_(case["wv"])
+        attn.to_out[0].weight.copy_(case["wo"]); attn.to_out[0].bias.copy_(case["bo"])
+        proc.to_k_ip.weight.copy_(case["wk_ip"]); proc.to_v_ip.weight.copy_(case["wv_ip"])
+    return attn.to(device, dtype), proc.to(device, dtype)
+
+
+def oracle_site(case: dict, dtype, scale=None) -> torch.Tensor:
+    r = lambda k: rounded(case[k], dtype)  # noqa: E731
+    return ipattn_oracle.ipattn_forward(r("x"), r("ctx"), r("wq"), r("wk"), r("wv"), r("wk_ip"), r("wv_ip"), r("wo"), r("bo"),
+                                        case["heads"], case["num_tokens"], case["scale"] if scale is None else scale)
+
+
+def random_site_case(bc, s, c, h, lt, la, scale=0.5, seed=0) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    n = lambda *shape, std=1.0: torch.randn(*shape, generator=g) * std  # noqa: E731
+    d = cases.DCTX
+    return dict(x=n(bc, s, c), ctx=n(bc, lt + la, d), wq=n(c, c, std=c ** -0.5), wk=n(c, d, std=1.5 * d ** -0.5),
+                wv=n(c, d, std=d ** -0.5), wk_ip=n(c, d, std=1.5 * d ** -0.5), wv_ip=n(c, d, std=d ** -0.5),
+                wo=n(c, c, std=c ** -0.5), bo=n(c, std=0.1), heads=h, num_tokens=lt, scale=scale)

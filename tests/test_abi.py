@@ -1,0 +1,71 @@
+"""libapx.so loads without a GPU and exports every symbol include/apx.h declares; the ctypes table matches the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from ap_adapter_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "apx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(apx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_functions():
+    fns = _header_functions()
+    assert "apx_ipattn_fwd" in fns and "apx_audiomae_fwd" in fns and "apx_ctx_kv" in fns and len(fns) >= 15
+
+
+def test_library_exports_every_header_symbol():
+    assert os.path.isfile(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [f for f in _header_functions() if not hasattr(lib, f)]
+    assert not missing, missing
+
+
+def test_ctypes_table_covers_header():
+    assert sorted(_lib.SYMBOLS) == _header_functions()
+
+
+def test_no_compute_queries_work_without_gpu():
+    lib = _lib.load()
+    assert lib.apx_version() >= 1
+    assert lib.apx_get_impl() == _lib.APX_IMPL_TC
+    assert lib.apx_set_impl(7) == 1 and b"unknown impl" in lib.apx_last_error()
+    # sizes are pure host arithmetic
+    assert lib.apx_ctx_kv_bytes(2, 8, 128, 256, 8) > 2 * 2 * 136 * 256 * 2
+    assert lib.apx_ctx_kv_bytes(2, 8, 128, 250, 8) == 0  # C not divisible by H
+    assert lib.apx_ipattn_workspace_bytes(2, 1000, 256) >= 2 * 2 * 1000 * 256 * 2
+    assert lib.apx_audiomae_workspace_bytes(1) > 513 * 3072 * 2
+
+
+def test_null_pointers_are_rejected_not_dereferenced():
+    lib = _lib.load()
+    rc = lib.apx_ipattn_fwd(None, None, None, None, None, None, 2, 64, 256, 8, 8, 8, 0.5, 0, None, 0, None)
+    assert rc == 1 and b"null pointer" in lib.apx_last_error()
+    rc = lib.apx_linear(None, 0, None, 0, None, None, 0, None, 0, 1, 64, 64, 0, 0, 0, None)
+    assert rc == 1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ap_adapter_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_cpu_tensors_fail_loudly():
+    import torch
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from oracle.ref_shims import StubAttention
+
+    proc = IPAttnProcessor2_0(256, "t", 768, num_tokens=8, scale=0.5)
+    attn = StubAttention(256, 768, 8)
+    with torch.no_grad(), pytest.raises(_lib.ApxError, match="no CPU fallback"):
+        proc(attn, torch.randn(2, 16, 256), encoder_hidden_states=torch.randn(2, 16, 768))

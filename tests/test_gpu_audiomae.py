@@ -1,0 +1,114 @@
+"""GPU parity of the AudioMAE encoder path (apx_patch_embed / apx_layernorm / apx_audiomae_* / apx_pool_tokens)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ap_adapter_b200 import _lib
+from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
+from oracle import audiomae_oracle as mae
+from oracle import cases
+
+from gpu_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+# fp16 tensor-core operands with fp32 accumulation / residual stream / LayerNorm over 12 blocks
+ENC_TOL = 4e-3
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return cases.mae_state_dict()
+
+
+@pytest.fixture(scope="module")
+def model(sd):
+    return AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd).cuda()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(cases.GOLDEN_DIR, "audiomae_reference.npz"))
+
+
+def test_patch_embed_stage(sd, model):
+    lib = _lib.load()
+    mel = cases.make_mel(batch=2).cuda()
+    w, _, _ = model.audiomae.model._weight_pack()
+    x = torch.empty(2, 513, 768, device="cuda")
+    _lib.check(lib.apx_patch_embed(_lib.ptr(mel), w.patch_wT, w.patch_b, w.pos_embed, w.cls_token, _lib.ptr(x), 2,
+                                   _lib.stream_ptr()), "apx_patch_embed")
+    ref = mae.patch_embed(cases.make_mel(batch=2).unsqueeze(1), sd)
+    assert rel_err(x, ref) < 1e-5
+
+
+def test_layernorm_stage():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1026, 768, generator=g) * 3 + 1
+    w, b = torch.randn(768, generator=g), torch.randn(768, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-6)
+    y = _lib.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, torch.float32)
+    assert rel_err(y, ref) < 1e-5
+    y16 = _lib.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6, torch.float16)
+    assert rel_err(y16, ref) < 1e-3
+
+
+@pytest.mark.parametrize("tp,fp", cases.POOLS)
+def test_pool_stage(model, tp, fp):
+    rep = torch.randn(3, 513, 768, generator=torch.Generator().manual_seed(tp * 8 + fp))
+    out = model.pool(rep.cuda(), time_pool=tp, freq_pool=fp)
+    ref = mae.pool(rep, tp, fp)
+    assert out.shape == ref.shape == (3, 512 // (tp * fp), 768)
+    assert rel_err(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["synth", "piano"])
+def test_encoder_matches_reference_output_fixture(tag, model, gold):
+    mel = cases.make_mel() if tag == "synth" else torch.from_numpy(gold["mel_piano_f16"]).float().unsqueeze(0)
+    n0 = _lib.launch_count()
+    rep = model.audiomae(mel.unsqueeze(1).cuda(), no_mask=True, no_average=True)
+    assert _lib.launch_count() - n0 >= 1 + 12 * 7 + 1
+    assert rep.shape == (1, 513, 768)
+    assert rel_err(rep[0, ::8], torch.from_numpy(gold[f"{tag}_encoder_rows"])) < ENC_TOL
+    for tp, fp in cases.POOLS:
+        emb, ones = model(mel.cuda(), time_pool=tp, freq_pool=fp)
+        assert emb.shape == (1, 512 // (tp * fp), 768) and ones.shape == emb.shape[:2] and bool((ones == 1).all())
+        sub = emb[0, ::4] if emb.shape[1] > 128 else emb[0]
+        assert rel_err(sub, torch.from_numpy(gold[f"{tag}_pool_{tp}x{fp}"])) < ENC_TOL
+
+
+def test_encoder_matches_oracle_batch_and_bf16(sd):
+    mel = cases.make_mel(seed=5, batch=3)
+    sd4 = {k: v for k, v in sd.items() if not k.startswith("blocks.") or int(k.split(".")[1]) < 4}
+    with torch.no_grad():
+        ref = mae.encoder(mel.unsqueeze(1), sd4, depth=4)
+    m16 = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd4, depth=4).cuda()
+    rep = m16.audiomae(mel.unsqueeze(1).cuda(), no_mask=True, no_average=True)
+    assert rel_err(rep, ref) < ENC_TOL
+    # clips are independent: clip 1 alone is bitwise what it is inside the batch
+    alone = m16.audiomae(mel[1:2].unsqueeze(1).cuda(), no_mask=True, no_average=True)
+    assert torch.equal(alone[0], rep[1])
+    mbf = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd4, depth=4).cuda().to(torch.bfloat16)
+    emb = mbf(mel.cuda(), time_pool=2, freq_pool=2)[0]
+    assert emb.dtype == torch.bfloat16
+    assert rel_err(emb, mae.pool(ref, 2, 2)) < 3e-2
+
+
+def test_zero_mel_unconditional_embedding(model, sd):
+    """pipeline_audioldm2.py:929: the unconditional branch encodes an all-zero mel."""
+    mel = torch.zeros(1, 1024, 128)
+    emb = model(mel.cuda(), time_pool=8, freq_pool=8)[0]
+    ref = mae.audiomae_forward(mel, sd, 8, 8)[0]
+    assert rel_err(emb, ref) < ENC_TOL
+
+
+def test_bad_arguments_raise(model):
+    with pytest.raises(_lib.ApxError, match="divide"):
+        model(cases.make_mel().cuda(), time_pool=3, freq_pool=2)
+    with pytest.raises(AssertionError):
+        model(torch.zeros(1, 1000, 128).cuda(), time_pool=2, freq_pool=2)
+    cpu_model = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=cases.mae_state_dict(depth=1), depth=1)
+    with pytest.raises(_lib.ApxError, match="CPU"):
+        cpu_model(cases.make_mel(), time_pool=2, freq_pool=2)

@@ -1,0 +1,185 @@
+"""Host-side logic that needs no GPU: processor registry of the restated UNet, checkpoint formats, the DDIM table,
+clip sharding, and the reference's own processors running inside the restated host graph."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ap_adapter_b200 import weights
+from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
+from ap_adapter_b200.pipeline import APAdapterDenoiser, DDIMScheduler, shard_range
+from ap_adapter_b200.unet import AUDIOLDM2_LARGE_CONFIG, AudioLDM2UNet2DConditionModel, build_attn_processors
+from oracle import ref_shims
+from oracle.ref_processors import OracleAttnProcessor2_0, OracleIPAttnProcessor2_0
+
+TINY = dict(block_out_channels=(32, 64, 96, 128), norm_num_groups=16)
+
+
+@pytest.fixture(scope="module")
+def tiny_unet():
+    torch.manual_seed(0)
+    return AudioLDM2UNet2DConditionModel(**TINY).eval()
+
+
+def test_registry_has_256_processors_and_32_adapter_sites():
+    with torch.device("meta"):
+        unet = AudioLDM2UNet2DConditionModel()
+    keys = list(unet.attn_processors)
+    assert len(keys) == 256 and all(k.endswith(".processor") for k in keys)
+    procs = build_attn_processors(unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=0.5)
+    sites = {k: p for k, p in procs.items() if isinstance(p, OracleIPAttnProcessor2_0)}
+    assert len(sites) == 32
+    by_c = {}
+    for k, p in sites.items():
+        by_c[p.hidden_size] = by_c.get(p.hidden_size, 0) + 1
+        assert ".attn2.processor" in k and k.split(".attentions.")[1].split(".")[0] in ("1", "5", "9")
+    assert by_c == {256: 10, 384: 10, 640: 12}
+    assert sum(p.numel() for s in sites.values() for p in s.parameters()) == 21_626_880
+
+
+def test_set_attn_processor_contract(tiny_unet):
+    procs = build_attn_processors(tiny_unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0)
+    with pytest.raises(ValueError, match="does not match"):
+        tiny_unet.set_attn_processor({k: v for k, v in list(procs.items())[:5]})
+    n = len(procs)
+    tiny_unet.set_attn_processor(procs)
+    assert len(procs) == 0  # the reference pops the entries (modeling_audioldm2.py:554-567)
+    reg = tiny_unet.attn_processors
+    assert len(reg) == n and sum(isinstance(p, OracleIPAttnProcessor2_0) for p in reg.values()) == 32
+    # registered Module processors are parameters of the UNet (AttnProcsLayers / optimizer see them)
+    assert any("processor.to_k_ip.weight" in k for k in tiny_unet.state_dict())
+    tiny_unet.set_attn_processor(OracleAttnProcessor2_0())
+
+
+def test_adapter_checkpoint_formats_roundtrip(tmp_path):
+    torch.manual_seed(1)
+    names = ["down_blocks.1.attentions.1.transformer_blocks.0.attn2.processor", "mid_block.attentions.1.transformer_blocks.1.attn2.processor"]
+    procs = {n: IPAttnProcessor2_0(64, n, 768, num_tokens=8) for n in names}
+    procs["x.attn1.processor"] = AttnProcessor2_0()
+    sd = weights.adapter_state_dict(procs)
+    assert sorted(sd) == sorted(f"{n}.to_{kv}_ip.weight" for n in names for kv in "kv")
+    path = tmp_path / "pytorch_model.bin"
+    torch.save({k: v.clone() for k, v in sd.items()}, path)
+    fresh = {n: IPAttnProcessor2_0(64, n, 768, num_tokens=8) for n in names}
+    assert weights.load_adapter_checkpoint(fresh, str(path), dtype=torch.float16) == 2
+    for n in names:
+        assert fresh[n].to_k_ip.weight.dtype == torch.float16
+        assert torch.equal(fresh[n].to_k_ip.weight.float(), procs[n].to_k_ip.weight.half().float())
+    with pytest.raises(KeyError):
+        weights.load_adapter_state_dict({"other.attn2.processor": IPAttnProcessor2_0(64, "o", 768)}, sd)
+    # copied_cross_attention/<site>_{k,v}.bin and do_copy=True
+    d = tmp_path / "copied_cross_attention"
+    k, v = torch.randn(64, 768).half(), torch.randn(64, 768).half()
+    weights.save_copied_cross_attention(str(d), names[0], k, v)
+    os.environ["APX_COPIED_CROSS_ATTENTION"] = str(d)
+    try:
+        p = IPAttnProcessor2_0(64, names[0], 768, num_tokens=8, do_copy=True)
+    finally:
+        del os.environ["APX_COPIED_CROSS_ATTENTION"]
+    assert p.to_k_ip.weight.dtype == torch.float32 and p.to_k_ip.weight.requires_grad
+    assert torch.equal(p.to_k_ip.weight.data, k.float()) and torch.equal(p.to_v_ip.weight.data, v.float())
+    assert [n for n, _ in p.named_parameters()] == ["to_k_ip.weight", "to_v_ip.weight"]
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present")
+def test_reads_the_shipped_copied_cross_attention_files():
+    site = "up_blocks.0.attentions.9.transformer_blocks.1.attn2.processor"
+    k, v = weights.load_copied_cross_attention(os.path.join(ref_shims.REF_ROOT, "copied_cross_attention"), site)
+    assert k.shape == (640, 768) and v.shape == (640, 768) and k.dtype == torch.float16
+
+
+def test_ddim_table_matches_stepwise_formula():
+    s = DDIMScheduler()
+    s.set_timesteps(200)
+    ts = s.timesteps
+    assert len(ts) == 200 and ts[0] == 996 and ts[-1] == 1 and (ts[:-1] - ts[1:] == 5).all()
+    coefs = s.coefficients()
+    g = torch.Generator().manual_seed(0)
+    x, eps = torch.randn(2, 8, 10, 4, generator=g), torch.randn(2, 8, 10, 4, generator=g)
+    for i in (0, 57, 199):
+        a_t = s.alphas_cumprod[ts[i]]
+        a_p = s.alphas_cumprod[ts[i] - 5] if ts[i] - 5 >= 0 else s.final_alpha_cumprod
+        x0 = (x - (1 - a_t).sqrt() * eps) / a_t.sqrt()
+        ref = a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps
+        assert torch.allclose(DDIMScheduler.step_with(coefs[i], eps, x), ref, atol=1e-5)
+        assert torch.allclose(s.step(eps, ts[i], x), ref, atol=1e-5)
+    # a perfect epsilon prediction recovers x0 at the end of the chain (size-independent property)
+    x0 = torch.randn(1, 8, 10, 4, generator=g)
+    noise = torch.randn(1, 8, 10, 4, generator=g)
+    a0 = s.alphas_cumprod[ts[0]]
+    xt = a0.sqrt() * x0 + (1 - a0).sqrt() * noise
+    for i in range(200):
+        xt = DDIMScheduler.step_with(coefs[i], noise, xt)
+    a_end = s.final_alpha_cumprod
+    assert torch.allclose(xt, a_end.sqrt() * x0 + (1 - a_end).sqrt() * noise, atol=1e-4)
+
+
+def test_shard_range_partitions_every_count():
+    for n in (1, 4, 7, 32, 33):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_unet_shapes_follow_the_reference_geometry(tiny_unet):
+    seen = []
+    tiny_unet.set_attn_processor(build_attn_processors(tiny_unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=0.5))
+
+    def hook(mod, args, kwargs, out):
+        if isinstance(mod.processor, OracleIPAttnProcessor2_0):
+            seen.append((args[0].shape[1], args[0].shape[2], kwargs["encoder_hidden_states"].shape[-1]))
+
+    hs = [m.register_forward_hook(hook, with_kwargs=True) for m in tiny_unet.modules() if hasattr(m, "set_processor")]
+    x = torch.randn(2, 8, 250, 16)
+    with torch.no_grad():
+        y = tiny_unet(x, torch.tensor(981), encoder_hidden_states=torch.randn(2, 8 + 32, 768),
+                      encoder_hidden_states_1=torch.randn(2, 6, 1024), encoder_attention_mask_1=torch.ones(2, 6))[0]
+    for h in hs:
+        h.remove()
+    assert y.shape == x.shape and torch.isfinite(y).all()
+    # 10 s latent 250x16 -> S = 1000 / 252 / 64 at the three adapter widths
+    assert len(seen) == 32
+    assert sorted(set(seen)) == [(64, 128, 768), (252, 96, 768), (1000, 64, 768)]
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present")
+def test_reference_processors_drop_into_the_restated_unet(tiny_unet):
+    """The reference's OWN IPAttnProcessor2_0 / AttnProcessor2_0, registered exactly as inference.py:22-59 does, run inside
+    the restated host graph and agree with the oracle processors: the duck-typed Attention exposes what they read."""
+    ap = ref_shims.load_attention_processor()
+    torch.manual_seed(3)
+    ref_procs = build_attn_processors(tiny_unet, ap.IPAttnProcessor2_0, ap.AttnProcessor2_0, ap_scale=0.6)
+    ora_procs = build_attn_processors(tiny_unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=0.6)
+    for k, p in ref_procs.items():
+        if hasattr(p, "to_k_ip"):
+            ora_procs[k].load_state_dict(p.state_dict())
+    x = torch.randn(2, 8, 40, 16)
+    kw = dict(encoder_hidden_states=torch.randn(2, 8 + 8, 768), encoder_hidden_states_1=torch.randn(2, 5, 1024),
+              encoder_attention_mask_1=torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1.0]]))
+    with torch.no_grad():
+        tiny_unet.set_attn_processor(ref_procs)
+        y_ref = tiny_unet(x, 500, **kw)[0]
+        tiny_unet.set_attn_processor(ora_procs)
+        y_ora = tiny_unet(x, 500, **kw)[0]
+    assert ((y_ref - y_ora).abs().max() / y_ref.abs().max()).item() < 1e-5
+
+
+def test_denoiser_conditioning_block_layout(tiny_unet):
+    """pipeline_audioldm2.py:935-949: rows [0,B) = [negative text | AudioMAE(zeros)], rows [B,2B) = [text | AudioMAE(mel)]."""
+    class FakeMAE(torch.nn.Module):
+        def forward(self, mel, time_pool=None, freq_pool=None):
+            n = 512 // (time_pool * freq_pool)
+            return [mel.mean().expand(mel.shape[0], n, 768).clone(), torch.ones(mel.shape[0], n)]
+
+    den = APAdapterDenoiser(tiny_unet, FakeMAE())
+    g = torch.randn(6, 8, 768)
+    out = den.audio_condition(torch.full((1, 1024, 128), 2.0), g, 4, 4)
+    assert out.shape == (6, 8 + 32, 768)
+    assert torch.equal(out[:, :8], g)
+    assert (out[:3, 8:] == 0).all() and (out[3:, 8:] == 2.0).all()
+    lat = den.prepare_latents(3, 1000, torch.float32, "cpu", torch.Generator().manual_seed(0))
+    assert lat.shape == (3, 8, 250, 16)
