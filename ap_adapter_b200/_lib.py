@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libapx.so")
 
 APX_F16, APX_BF16, APX_F32 = 0, 1, 2
 APX_EPI_NONE, APX_EPI_GELU = 0, 1
-APX_IMPL_TC, APX_IMPL_SIMT = 0, 1
+APX_IMPL_TC, APX_IMPL_SIMT, APX_IMPL_TC_UNFUSED = 0, 1, 2
 
 # every symbol include/apx.h declares: (restype, argtypes)
 _P, _I, _L, _F, _Z = c_void_p, c_int, c_int64, c_float, c_size_t
@@ -47,7 +47,10 @@ SYMBOLS = {
     "apx_ctx_kv_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "apx_ctx_kv": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "apx_ipattn_workspace_bytes": (_Z, [_I, _I, _I]),
-    "apx_ipattn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "apx_ipattn_pack_bytes": (_Z, [_I, _I]),
+    "apx_ipattn_pack": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "apx_ipattn_fused_ok": (_I, [_I, _I, _I, _I]),
+    "apx_ipattn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_audiomae_workspace_bytes": (_Z, [_I]),
     "apx_audiomae_fwd": (_I, [_P, POINTER(VitWeights), _P, _I, _I, _I, _P, _Z, _P]),
     "apx_audiomae_encode": (_I, [_P, POINTER(VitWeights), _P, _I, _P, _Z, _P]),

@@ -111,6 +111,7 @@ class IPAttnProcessor2_0(nn.Module):
         self.to_v_ip = nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
         self.name = name
         self._ctx_cache = None  # (key, cache blob, keyed tensors)
+        self._w_cache = None    # (key, (wq, wo, packed blob or None), keyed tensors)
         if do_copy:
             from .weights import load_copied_cross_attention
             k_weight, v_weight = load_copied_cross_attention(_copied_weight_dir(), name)
@@ -126,6 +127,31 @@ class IPAttnProcessor2_0(nn.Module):
 
     def invalidate_cache(self):
         self._ctx_cache = None
+        self._w_cache = None
+
+    def _site_weights(self, attn, heads: int, dtype: torch.dtype):
+        """(to_q.weight, to_out[0].weight, packed blob) in the kernel dtype; the blob is the one-time re-layout the
+        fused kernel streams per head (apx_ipattn_pack), None when the fused kernel does not cover (C, heads).
+        Cached per weight version: the UNet is frozen, so this runs once."""
+        wq_p, wo_p = attn.to_q.weight, attn.to_out[0].weight
+        key = (self._tkey(wq_p), self._tkey(wo_p), heads, dtype)
+        if self._w_cache is not None and self._w_cache[0] == key:
+            return self._w_cache[1]
+        lib = _lib.load()
+        c = self.hidden_size
+        wq = wq_p.detach().to(dtype).contiguous()
+        wo = wo_p.detach().to(dtype).contiguous()
+        if tuple(wq.shape) != (c, c) or tuple(wo.shape) != (c, c):
+            raise _lib.ApxError(f"{self.name}: to_q / to_out weights {tuple(wq.shape)} / {tuple(wo.shape)} != ({c}, {c})")
+        pack = None
+        nbytes = lib.apx_ipattn_pack_bytes(c, heads)
+        if nbytes:
+            pack = torch.empty(nbytes, dtype=torch.uint8, device=wq.device)
+            with torch.cuda.device(wq.device):
+                _lib.check(lib.apx_ipattn_pack(_lib.ptr(wq), _lib.ptr(wo), _lib.ptr(pack), c, heads, _lib.dtype_code(dtype),
+                                               _lib.stream_ptr()), "apx_ipattn_pack")
+        self._w_cache = (key, (wq, wo, pack), (wq_p, wo_p))
+        return self._w_cache[1]
 
     def _context_cache(self, attn, ctx: torch.Tensor, heads: int, dtype: torch.dtype) -> torch.Tensor:
         wk, wv = attn.to_k.weight, attn.to_v.weight
@@ -203,12 +229,9 @@ class IPAttnProcessor2_0(nn.Module):
 
         lib = _lib.load()
         cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
-        wq = attn.to_q.weight.detach()
-        wo = attn.to_out[0].weight.detach()
         if getattr(attn.to_q, "bias", None) is not None:
             raise _lib.ApxError(f"{self.name}: to_q with bias is not implemented (attention_bias=False in AudioLDM2)")
-        wq = wq if wq.dtype == dtype and wq.is_contiguous() else wq.to(dtype).contiguous()
-        wo = wo if wo.dtype == dtype and wo.is_contiguous() else wo.to(dtype).contiguous()
+        wq, wo, wpack = self._site_weights(attn, heads, dtype)
         bo = attn.to_out[0].bias
         if bo is not None:
             bo = self._bias_f32(bo)
@@ -216,9 +239,9 @@ class IPAttnProcessor2_0(nn.Module):
         wsb = lib.apx_ipattn_workspace_bytes(bc, s, c)
         work = _lib.workspace(wsb, x.device, "ipattn")
         with torch.cuda.device(x.device):
-            _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(bo), _lib.ptr(y),
-                                          bc, s, c, heads, lt, la, float(self.scale), _lib.dtype_code(dtype), _lib.ptr(work),
-                                          wsb, _lib.stream_ptr()), "apx_ipattn_fwd")
+            _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(wpack), _lib.ptr(bo),
+                                          _lib.ptr(y), bc, s, c, heads, lt, la, float(self.scale), _lib.dtype_code(dtype),
+                                          _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_ipattn_fwd")
         hidden_states = attn.to_out[1](y)  # dropout (p = 0)
         if input_ndim == 4:
             hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)

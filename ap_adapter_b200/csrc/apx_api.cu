@@ -96,7 +96,7 @@ using namespace apx;
 extern "C" {
 
 const char* apx_last_error(void) { return g_err; }
-int apx_version(void) { return 1; }
+int apx_version(void) { return 2; }
 uint64_t apx_launch_count(void) { return g_launches.load(); }
 
 int apx_device_ok(void) {
@@ -114,7 +114,8 @@ int apx_device_ok(void) {
 }
 
 int apx_set_impl(int impl) {
-    APX_REQUIRE(impl == APX_IMPL_TC || impl == APX_IMPL_SIMT, APX_EINVAL, "apx_set_impl: unknown impl %d", impl);
+    APX_REQUIRE(impl == APX_IMPL_TC || impl == APX_IMPL_SIMT || impl == APX_IMPL_TC_UNFUSED, APX_EINVAL,
+                "apx_set_impl: unknown impl %d", impl);
     g_impl.store(impl);
     return APX_OK;
 }
@@ -191,22 +192,40 @@ size_t apx_ipattn_workspace_bytes(int Bc, int S, int C) {
     return 2 * align_up(static_cast<size_t>(Bc) * S * C * 2, 256);
 }
 
-int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const float* bo, void* Y, int Bc,
-                   int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
+size_t apx_ipattn_pack_bytes(int C, int H) {
+    const FusedGeom g = fused_geom(C, H);
+    return g.nsplit ? g.total : 0;
+}
+int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, int dtype, void* stream) {
+    APX_REQUIRE(Wq && Wo && wpack, APX_EINVAL, "apx_ipattn_pack: null pointer");
+    return ipattn_pack_weights(Wq, Wo, wpack, C, H, dtype, static_cast<cudaStream_t>(stream));
+}
+int apx_ipattn_fused_ok(int C, int H, int Lt, int La) { return ipattn_fused_supported(C, H, Lt, La) ? 1 : 0; }
+
+int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
+                   void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
                    size_t workspace_bytes, void* stream) {
-    APX_REQUIRE(X && Wq && cache && Wo && Y && workspace, APX_EINVAL, "apx_ipattn_fwd: null pointer");
+    APX_REQUIRE(X && cache && Y, APX_EINVAL, "apx_ipattn_fwd: null pointer");
     APX_REQUIRE(Bc > 0 && S > 0 && C > 0 && H > 0 && C % H == 0 && Lt >= 0 && La >= 0 && Lt + La > 0, APX_EINVAL,
                 "apx_ipattn_fwd: bad shape Bc=%d S=%d C=%d H=%d Lt=%d La=%d", Bc, S, C, H, Lt, La);
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_ipattn_fwd: dtype %d", dtype);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const CtxCacheLayout lay = ctx_cache_layout(Bc, Lt, La, C, H);
+    const uint8_t* cb = static_cast<const uint8_t*>(cache);
+    // the product path: one fused tcgen05 kernel per site
+    if (current_impl() == APX_IMPL_TC && wpack && ipattn_fused_supported(C, H, Lt, La))
+        return ipattn_fused(X, wpack, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, st);
+
+    APX_REQUIRE(Wq && Wo && workspace, APX_EINVAL, "apx_ipattn_fwd: the three-kernel path needs Wq, Wo and a workspace");
+    APX_REQUIRE((C / H) % 8 == 0 && (C / H) <= 80, APX_EUNSUPPORTED,
+                "apx_ipattn_fwd: head dim %d (need d %% 8 == 0, d <= 80)", C / H);
+    APX_REQUIRE(C % 64 == 0, APX_EUNSUPPORTED, "apx_ipattn_fwd: C=%d must be a multiple of 64", C);
     APX_REQUIRE(workspace_bytes >= apx_ipattn_workspace_bytes(Bc, S, C), APX_EWORKSPACE,
                 "apx_ipattn_fwd: workspace %zu < %zu", workspace_bytes, apx_ipattn_workspace_bytes(Bc, S, C));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int M = Bc * S, d = C / H, L = Lt + La;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     void* q = ws;
     void* o = ws + align_up(static_cast<size_t>(M) * C * 2, 256);
-    const CtxCacheLayout lay = ctx_cache_layout(Bc, Lt, La, C, H);
-    const uint8_t* cb = static_cast<const uint8_t*>(cache);
 
     int rc = apx_linear(X, C, Wq, C, nullptr, nullptr, 0, q, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
     if (rc) return rc;

@@ -58,6 +58,18 @@ int ipattn_core_tc(const void* Q, const void* cache, void* O, int Bc, int S, int
 int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void* cache, int Bc, int Lt, int La,
             int C, int H, int dtype, cudaStream_t st);
 
+// ---- fused adapter site (apx_ipattn_fused.cu) ----------------------------------------------------------
+// Geometry of the pre-packed Wq / Wo blob consumed by the fused kernel; nsplit == 0 means "not covered".
+struct FusedGeom {
+    int C, H, d, d_pad, nsplit, CN;
+    size_t wq_chunk_bytes, wq_head_bytes, wo_tile_bytes, wq_off, wo_off, total;
+};
+FusedGeom fused_geom(int C, int H);
+bool ipattn_fused_supported(int C, int H, int Lt, int La);
+int ipattn_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
+int ipattn_fused(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S,
+                 int C, int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st);
+
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
               int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,

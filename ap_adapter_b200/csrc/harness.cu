@@ -214,33 +214,48 @@ static int case_site(int Bc, int S, int C, int H, int Lt, int La, int dt, bool c
     uint16_t *dX = dev(X), *dctx = dev(ctx), *dWq = dev(Wq), *dWo = dev(Wo), *dWk = dev(Wk), *dWv = dev(Wv), *dWki = dev(Wki), *dWvi = dev(Wvi);
     float* dbo = dev(bo);
     const size_t cbytes = apx_ctx_kv_bytes(Bc, Lt, La, C, H), wsb = std::max(apx_ctx_kv_workspace_bytes(Bc, Lt, La, C), apx_ipattn_workspace_bytes(Bc, S, C));
-    void *cache[2], *ws, *Y[2];
-    for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&cache[i], cbytes)); CK(cudaMalloc(&Y[i], (size_t)Bc * S * C * 2)); CK(cudaMemset(Y[i], 0xFF, (size_t)Bc * S * C * 2)); }
+    void *cache[3], *ws, *Y[3], *wpack = nullptr;
+    for (int i = 0; i < 3; ++i) { CK(cudaMalloc(&cache[i], cbytes)); CK(cudaMalloc(&Y[i], (size_t)Bc * S * C * 2)); CK(cudaMemset(Y[i], 0xFF, (size_t)Bc * S * C * 2)); }
     CK(cudaMalloc(&ws, wsb));
+    const bool fused = apx_ipattn_fused_ok(C, H, Lt, La) && apx_ipattn_pack_bytes(C, H) > 0;
+    if (fused) {
+        CK(cudaMalloc(&wpack, apx_ipattn_pack_bytes(C, H)));
+        AK(apx_ipattn_pack(dWq, dWo, wpack, C, H, dt, nullptr));
+    }
+    // i = 0: product path (fused kernel when covered), 1: CUDA-core cross-check, 2: three tcgen05 kernels
     auto run = [&](int impl, int i, bool build_cache) -> int {
         AK(apx_set_impl(impl));
         if (build_cache) AK(apx_ctx_kv(dctx, dWk, dWv, dWki, dWvi, cache[i], Bc, Lt, La, D, C, H, dt, ws, wsb, nullptr));
-        AK(apx_ipattn_fwd(dX, dWq, cache[i], dWo, dbo, Y[i], Bc, S, C, H, Lt, La, ap, dt, ws, wsb, nullptr));
+        AK(apx_ipattn_fwd(dX, dWq, cache[i], dWo, impl == APX_IMPL_TC ? wpack : nullptr, dbo, Y[i], Bc, S, C, H, Lt, La, ap, dt, ws, wsb, nullptr));
         return 0;
     };
     if (run(APX_IMPL_SIMT, 1, true)) return 1;
     CK(cudaDeviceSynchronize());
+    if (run(APX_IMPL_TC_UNFUSED, 2, true)) return 1;
+    CK(cudaDeviceSynchronize());
     if (run(APX_IMPL_TC, 0, true)) return 1;
     CK(cudaDeviceSynchronize());
     auto y_tc = tofloat(host((uint16_t*)Y[0], (size_t)Bc * S * C), dt), y_simt = tofloat(host((uint16_t*)Y[1], (size_t)Bc * S * C), dt);
+    auto y_un = tofloat(host((uint16_t*)Y[2], (size_t)Bc * S * C), dt);
     const float tol = dt == APX_BF16 ? 2e-2f : 4e-3f;
     int fails = 0;
+    printf("  product path: %s\n", fused ? "FUSED kernel" : "three kernels (shape not covered by the fused kernel)");
     if (cpu_ref) {
         std::vector<float> ref;
         cpu_site(tofloat(X, dt), tofloat(Wq, dt), tofloat(ctx, dt), tofloat(Wk, dt), tofloat(Wv, dt), tofloat(Wki, dt), tofloat(Wvi, dt), tofloat(Wo, dt), bo, Bc, S, C, H, Lt, La, D, ap, ref);
         fails += compare("simt vs cpu", y_simt, ref, Bc * S, C, tol);
-        fails += compare("tcgen05 vs cpu", y_tc, ref, Bc * S, C, tol);
+        fails += compare("tcgen05 unfused vs cpu", y_un, ref, Bc * S, C, tol);
+        fails += compare("tcgen05 product vs cpu", y_tc, ref, Bc * S, C, tol);
     } else {
-        fails += compare("tcgen05 vs simt", y_tc, y_simt, Bc * S, C, tol);
+        fails += compare("tcgen05 unfused vs simt", y_un, y_simt, Bc * S, C, tol);
+        fails += compare("tcgen05 product vs simt", y_tc, y_simt, Bc * S, C, tol);
     }
     const float t_tc = time_ms([&] { return run(APX_IMPL_TC, 0, false); });
+    const float t_un = time_ms([&] { return run(APX_IMPL_TC_UNFUSED, 2, false); });
     const float t_simt = time_ms([&] { return run(APX_IMPL_SIMT, 1, false); }, 5);
-    printf("  time per site call: tcgen05 %.1f us   simt %.1f us\n", t_tc * 1e3, t_simt * 1e3);
+    const double fl = 4.0 * Bc * S * (double)C * C + 4.0 * Bc * S * (double)L * C;
+    printf("  time per site call: product %.1f us (%.1f TFLOP/s)   unfused %.1f us   simt %.1f us\n", t_tc * 1e3, fl / t_tc * 1e-9, t_un * 1e3, t_simt * 1e3);
+    AK(apx_set_impl(APX_IMPL_TC));
     return fails;
 }
 
@@ -274,7 +289,11 @@ int main(int argc, char** argv) {
     S("site_1x128x256_8+512_f16_cpu", 1, 128, 256, 8, 8, 512, APX_F16, true);
     S("site_1x128x256_textonly_f16_cpu", 1, 128, 256, 8, 8, 0, APX_F16, true);
     S("site_1x128x256_audioonly_f16_cpu", 1, 128, 256, 8, 0, 40, APX_F16, true);
+    S("site_3x129x256_8+24_bf16_cpu", 3, 129, 256, 8, 8, 24, APX_BF16, true);
+    S("site_2x96x512_16h_8+32_f16_cpu", 2, 96, 512, 16, 8, 32, APX_F16, true);
     S("site_2x1000x256_8+128_f16", 2, 1000, 256, 8, 8, 128, APX_F16, false);
+    S("site_2x1000x256_8+32_f16", 2, 1000, 256, 8, 8, 32, APX_F16, false);
+    S("site_2x1000x256_8+8_f16", 2, 1000, 256, 8, 8, 8, APX_F16, false);
     S("site_2x252x384_8+128_f16", 2, 252, 384, 8, 8, 128, APX_F16, false);
     S("site_2x64x640_8+128_f16", 2, 64, 640, 8, 8, 128, APX_F16, false);
     S("site_16x1000x256_8+128_f16", 16, 1000, 256, 8, 8, 128, APX_F16, false);

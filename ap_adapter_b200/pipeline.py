@@ -173,9 +173,12 @@ class APAdapterDenoiser(nn.Module):
             for _ in range(2):
                 self.denoise_step(st["latents"], st["t"], st["coef"], gpe, pe, mask, guidance_scale)
         torch.cuda.current_stream(dev).wait_stream(side)
+        from . import _lib
         graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
             st["out"] = self.denoise_step(st["latents"], st["t"], st["coef"], gpe, pe, mask, guidance_scale)
+        st["apx_launches_per_step"] = _lib.launch_count() - n0  # libapx kernels captured in one denoise step
         st["graph"] = graph
         self._graph = st
         return st

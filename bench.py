@@ -177,13 +177,19 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
     wsb = max(lib.apx_ctx_kv_workspace_bytes(bc, LT, LA, c), lib.apx_ipattn_workspace_bytes(bc, s, c))
     ws = torch.empty(r, (wsb + 255) // 256 * 256, dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr()
+    pbytes = lib.apx_ipattn_pack_bytes(c, h)
+    fused = bool(pbytes) and lib.apx_ipattn_fused_ok(c, h, LT, LA) == 1
+    pack = torch.empty(r, max(256, (pbytes + 255) // 256 * 256), dtype=torch.uint8, device=dev)
     for i in range(r):
+        if fused:
+            _lib.check(lib.apx_ipattn_pack(_lib.ptr(wq[i]), _lib.ptr(wo[i]), _lib.ptr(pack[i]), c, h, 0, st), "apx_ipattn_pack")
         _lib.check(lib.apx_ctx_kv(_lib.ptr(ctx), *[_lib.ptr(w) for w in wkv], _lib.ptr(cache[i]), bc, LT, LA, d, c, h, 0,
                                   _lib.ptr(ws[i]), wsb, st), "apx_ctx_kv")
 
     def launch(i):
-        _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x[i]), _lib.ptr(wq[i]), _lib.ptr(cache[i]), _lib.ptr(wo[i]), _lib.ptr(bo),
-                                      _lib.ptr(y[i]), bc, s, c, h, LT, LA, AP_SCALE, 0, _lib.ptr(ws[i]), wsb, st), "apx_ipattn_fwd")
+        _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x[i]), _lib.ptr(wq[i]), _lib.ptr(cache[i]), _lib.ptr(wo[i]),
+                                      _lib.ptr(pack[i]) if fused else None, _lib.ptr(bo), _lib.ptr(y[i]), bc, s, c, h, LT, LA,
+                                      AP_SCALE, 0, _lib.ptr(ws[i]), wsb, st), "apx_ipattn_fwd")
 
     for i in range(r):
         launch(i)
@@ -210,7 +216,9 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
         achieved, peak, unit = flops / (us * 1e-6) / 1e12, pk["tflops"], "TFLOP/s"
     else:
         achieved, peak, unit = byts / (us * 1e-6) / 1e9, pk["hbm_gbs"], "GB/s"
-    return {"kernel": f"adapter site via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
+    name = "ipattn_fused_kernel (to_q + dual softmax(QK^T)V + ap_scale add + to_out in one tcgen05 kernel)" if fused else \
+        "gemm_tc + ipattn_core + gemm_tc"
+    return {"kernel": f"{name} via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
             "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
             "traffic": None, "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
             "floor_us": round(1e6 * max(t_tensor, t_hbm), 3), "peak_source": pk["source"], "operand_copies_rotated": r}
@@ -250,9 +258,8 @@ def run_ours(args) -> dict:
     ts, coefs = den.scheduler.timesteps, den.scheduler.coefficients(dev)
 
     with torch.no_grad():
-        n0 = _lib.launch_count()
         graph = den._step_graph(lat0, gpe, pe, mask, GUIDANCE)  # 2 eager warm-up steps + 1 captured step
-        per_step_launches = (_lib.launch_count() - n0) // 3
+        per_step_launches = graph["apx_launches_per_step"]
 
         def step(i):
             graph["t"].copy_(ts[i % INFER_STEPS])

@@ -11,6 +11,7 @@
  * Reference interfaces replaced (paths relative to the AP-adapter repository):
  *   apx_ipattn_fwd        APadapter/ap_adapter/attention_processor.py:347-470
  *                         (IPAttnProcessor2_0.__call__: to_q, two SDPAs, scale-add, to_out)
+ *   apx_ipattn_pack       one-time re-layout of attn.to_q.weight / attn.to_out[0].weight (:387,:457) for the fused kernel
  *   apx_ctx_kv            attention_processor.py:400-415,435-439 (to_k/to_v on the text rows,
  *                         to_k_ip/to_v_ip on the audio rows; timestep-invariant, cached)
  *   apx_linear            the nn.Linear dispatches on the path (attention_processor.py:387,457;
@@ -50,13 +51,14 @@ extern "C" {
 #define APX_EPI_GELU      1   /* exact erf GELU, applied after the bias                      */
 
 /* ---- kernel families ---------------------------------------------------------------- */
-#define APX_IMPL_TC    0      /* tcgen05 + TMA + TMEM (product path)                         */
-#define APX_IMPL_SIMT  1      /* plain CUDA-core kernels: device-side cross-check for tests   */
+#define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; fused site kernel when packed weights are given) */
+#define APX_IMPL_SIMT         1   /* plain CUDA-core kernels: device-side cross-check for tests                     */
+#define APX_IMPL_TC_UNFUSED   2   /* tcgen05 path as three kernels (to_q GEMM, attention core, to_out GEMM)         */
 
 const char* apx_last_error(void);
 int         apx_version(void);            /* ABI version, bumps on any signature change   */
 int         apx_device_ok(void);          /* 1 iff the current device is compute 10.x      */
-int         apx_set_impl(int impl);       /* APX_IMPL_TC (default) or APX_IMPL_SIMT        */
+int         apx_set_impl(int impl);       /* APX_IMPL_TC (default), _SIMT or _TC_UNFUSED   */
 int         apx_get_impl(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches)     */
 uint64_t    apx_launch_count(void);
@@ -103,14 +105,27 @@ int apx_ctx_kv(const void* ctx, const void* Wk, const void* Wv, const void* Wk_i
 size_t apx_ctx_kv_workspace_bytes(int Bc, int Lt, int La, int C);
 
 /*
- * One adapter site, one denoise step:
+ * Pre-packed to_q / to_out weights of one adapter site for the fused kernel (build once per weight version).
+ * Wq, Wo [C, C] `dtype` contiguous (attn.to_q.weight, attn.to_out[0].weight).  apx_ipattn_pack_bytes returns 0
+ * when the fused kernel does not cover (C, H) (then pass wpack = NULL below).
+ */
+size_t apx_ipattn_pack_bytes(int C, int H);
+int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, int dtype, void* stream);
+/* 1 iff apx_ipattn_fwd runs this shape as the single fused kernel when given a pack */
+int apx_ipattn_fused_ok(int C, int H, int Lt, int La);
+
+/*
+ * One adapter site, one denoise step (attention_processor.py:387-459):
  *   Y = ( SDPA(X Wq^T, K_t, V_t) + ap_scale · SDPA(X Wq^T, K_a, V_a) ) Wo^T + bo
  * X, Y [Bc, S, C] contiguous `dtype`; Wq, Wo [C, C] `dtype`; bo fp32[C] or NULL;
- * `cache` from apx_ctx_kv with identical (Bc, Lt, La, C, H).
+ * `cache` from apx_ctx_kv with identical (Bc, Lt, La, C, H); `wpack` from apx_ipattn_pack or NULL.
+ * With a pack and a covered shape this is ONE tcgen05 kernel (to_q + both softmax(QK^T)V + ap_scale add + to_out);
+ * otherwise three (GEMM, attention core, GEMM) using `workspace` for Q and O.  Wq / Wo may be NULL when the fused
+ * kernel is guaranteed (apx_ipattn_fused_ok).
  * workspace: apx_ipattn_workspace_bytes(Bc, S, C) bytes.
  */
 size_t apx_ipattn_workspace_bytes(int Bc, int S, int C);
-int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const float* bo,
+int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
                    void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
                    void* workspace, size_t workspace_bytes, void* stream);
 

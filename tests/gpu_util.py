@@ -38,6 +38,31 @@ def oracle_site(case: dict, dtype, scale=None) -> torch.Tensor:
                                         case["heads"], case["num_tokens"], case["scale"] if scale is None else scale)
 
 
+def torch_lowp_site(case: dict, dtype, scale=None, device="cuda") -> torch.Tensor:
+    """The reference algorithm (attention_processor.py:387-459) run by stock PyTorch ops in `dtype` on the GPU — nn.Linear
+    + F.scaled_dot_product_attention, i.e. what the reference's own fp16 inference path computes.  Its distance to the
+    fp32 oracle is the rounding noise inherent to 16-bit Q/K/V/P storage for this case."""
+    import torch.nn.functional as F
+
+    t = lambda k: case[k].to(device, dtype)  # noqa: E731
+    x, ctx = t("x"), t("ctx")
+    if ctx.dim() < 3:
+        ctx = ctx.unsqueeze(0)
+    h, nt = case["heads"], case["num_tokens"]
+    b = ctx.shape[0]
+    q = F.linear(x, t("wq"))
+    c = q.shape[-1]
+    sp = lambda z: z.view(b, -1, h, c // h).transpose(1, 2)  # noqa: E731
+    text, audio = ctx[:, :nt], ctx[:, nt:]
+    o = torch.zeros_like(q)
+    if text.shape[1]:
+        o = F.scaled_dot_product_attention(sp(q), sp(F.linear(text, t("wk"))), sp(F.linear(text, t("wv")))).transpose(1, 2).reshape(b, -1, c)
+    if audio.shape[1]:
+        oa = F.scaled_dot_product_attention(sp(q), sp(F.linear(audio, t("wk_ip"))), sp(F.linear(audio, t("wv_ip")))).transpose(1, 2).reshape(b, -1, c)
+        o = o + (case["scale"] if scale is None else scale) * oa
+    return F.linear(o, t("wo"), t("bo"))
+
+
 def random_site_case(bc, s, c, h, lt, la, scale=0.5, seed=0) -> dict:
     g = torch.Generator().manual_seed(seed)
     n = lambda *shape, std=1.0: torch.randn(*shape, generator=g) * std  # noqa: E731

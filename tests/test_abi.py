@@ -42,11 +42,17 @@ def test_no_compute_queries_work_without_gpu():
     assert lib.apx_ctx_kv_bytes(2, 8, 128, 250, 8) == 0  # C not divisible by H
     assert lib.apx_ipattn_workspace_bytes(2, 1000, 256) >= 2 * 2 * 1000 * 256 * 2
     assert lib.apx_audiomae_workspace_bytes(1) > 513 * 3072 * 2
+    # fused-kernel coverage and packed-weight size: [H][C/64][8][d_pad][8] + [nsplit][H][d_pad/8][CN][8] 16-bit elements
+    assert lib.apx_ipattn_pack_bytes(256, 8) == 2 * 256 * 256 * 2
+    assert lib.apx_ipattn_pack_bytes(320, 8) == 2 * (8 * 48 * 320 + 2 * 8 * 48 * 160)   # d = 40 padded to 48
+    assert lib.apx_ipattn_pack_bytes(640, 8) == 0                                        # Y accumulator exceeds TMEM
+    assert lib.apx_ipattn_fused_ok(256, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(384, 8, 8, 128) == 1
+    assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(640, 8, 8, 8) == 0
 
 
 def test_null_pointers_are_rejected_not_dereferenced():
     lib = _lib.load()
-    rc = lib.apx_ipattn_fwd(None, None, None, None, None, None, 2, 64, 256, 8, 8, 8, 0.5, 0, None, 0, None)
+    rc = lib.apx_ipattn_fwd(None, None, None, None, None, None, None, 2, 64, 256, 8, 8, 8, 0.5, 0, None, 0, None)
     assert rc == 1 and b"null pointer" in lib.apx_last_error()
     rc = lib.apx_linear(None, 0, None, 0, None, None, 0, None, 0, 1, 64, 64, 0, 0, 0, None)
     assert rc == 1
