@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace apx {
@@ -192,15 +193,39 @@ size_t apx_ipattn_workspace_bytes(int Bc, int S, int C) {
     return 2 * align_up(static_cast<size_t>(Bc) * S * C * 2, 256);
 }
 
+// The pack blob holds the site kernel's re-layout of Wq / Wo (apx_ipattn_site.cu); shapes it does not cover take the
+// three-kernel path, which reads the weights as they are.  (The first-generation fused kernel, one head at a time, was
+// retired in round 1: at every shape it covered it was slower than the three-kernel path — profiles/r1_*.)
+struct PackLayout { size_t site_off, site_bytes, total; };
+static PackLayout pack_layout(int C, int H) {
+    PackLayout l;
+    const SiteGeom sg = site_geom(C, H);
+    l.site_off = 0;
+    l.site_bytes = sg.ok ? sg.total : 0;
+    l.total = l.site_bytes;
+    return l;
+}
+// APX_SITE_KERNEL=0 forces the three-kernel path (A/B measurements only)
+static bool site_kernel_enabled() {
+    static const bool on = [] { const char* e = getenv("APX_SITE_KERNEL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 size_t apx_ipattn_pack_bytes(int C, int H) {
-    const FusedGeom g = fused_geom(C, H);
-    return g.nsplit ? g.total : 0;
+    if (C <= 0 || H <= 0 || C % H) return 0;
+    return pack_layout(C, H).total;
 }
 int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, int dtype, void* stream) {
     APX_REQUIRE(Wq && Wo && wpack, APX_EINVAL, "apx_ipattn_pack: null pointer");
-    return ipattn_pack_weights(Wq, Wo, wpack, C, H, dtype, static_cast<cudaStream_t>(stream));
+    APX_REQUIRE(C > 0 && H > 0 && C % H == 0, APX_EINVAL, "apx_ipattn_pack: bad shape C=%d H=%d", C, H);
+    const PackLayout l = pack_layout(C, H);
+    APX_REQUIRE(l.total > 0, APX_EUNSUPPORTED, "apx_ipattn_pack: no single-kernel path covers C=%d H=%d", C, H);
+    return ipattn_site_pack_weights(Wq, Wo, static_cast<uint8_t*>(wpack) + l.site_off, C, H, dtype, static_cast<cudaStream_t>(stream));
 }
-int apx_ipattn_fused_ok(int C, int H, int Lt, int La) { return ipattn_fused_supported(C, H, Lt, La) ? 1 : 0; }
+int apx_ipattn_fused_ok(int C, int H, int Lt, int La) {
+    if (C <= 0 || H <= 0 || C % H) return 0;
+    return ipattn_site_supported(C, H, Lt, La) ? 1 : 0;
+}
 
 int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
                    void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
@@ -213,8 +238,12 @@ int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void*
     const CtxCacheLayout lay = ctx_cache_layout(Bc, Lt, La, C, H);
     const uint8_t* cb = static_cast<const uint8_t*>(cache);
     // the product path: one fused tcgen05 kernel per site
-    if (current_impl() == APX_IMPL_TC && wpack && ipattn_fused_supported(C, H, Lt, La))
-        return ipattn_fused(X, wpack, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, st);
+    if (current_impl() == APX_IMPL_TC && wpack) {
+        const PackLayout pl = pack_layout(C, H);
+        if (pl.site_bytes && site_kernel_enabled() && ipattn_site_supported(C, H, Lt, La))
+            return ipattn_site(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
+                               La, ap_scale, dtype, st);
+    }
 
     APX_REQUIRE(Wq && Wo && workspace, APX_EINVAL, "apx_ipattn_fwd: the three-kernel path needs Wq, Wo and a workspace");
     APX_REQUIRE((C / H) % 8 == 0 && (C / H) <= 80, APX_EUNSUPPORTED,

@@ -26,9 +26,11 @@ KvPackGeom kv_pack_geom(int Lt, int La, int C, int H) {
     g.L_pad = g.Lt_pad + g.La_pad;
     g.d = C / H;
     g.d_pad = (g.d + 15) / 16 * 16;
+    g.dv_pad = g.d_pad + 16;
     g.k_tile_bytes = static_cast<size_t>(g.d_pad) * g.L_pad * 2;
     g.v_tile_bytes = g.k_tile_bytes;
-    g.bytes_per_bh = g.k_tile_bytes + g.v_tile_bytes;
+    g.vx_tile_bytes = static_cast<size_t>(g.dv_pad) * g.L_pad * 2;
+    g.bytes_per_bh = g.k_tile_bytes + g.v_tile_bytes + g.vx_tile_bytes;
     return g;
 }
 
@@ -44,7 +46,8 @@ struct AttnArgs {
     float ap_scale;
     float scale_log2;      // log2(e) / sqrt(d)
     int fmt;               // 0 f16, 1 bf16
-    uint32_t k_tile_bytes, bytes_per_bh;
+    uint32_t k_tile_bytes, v_tile_bytes, bytes_per_bh;
+    int dv_pad;
     const uint16_t* Q;     // only read when q_manual != 0
     int q_manual;          // debug hedge: stage the Q tile with ld.global/st.shared instead of the 4-D TMA
 };
@@ -58,7 +61,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + q_bytes;
     uint8_t* sV = sK + a.k_tile_bytes;
-    uint8_t* sP = sV + a.k_tile_bytes;
+    uint8_t* sP = sV + a.v_tile_bytes;
     uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 128 * CHUNK * 2);
     uint64_t* bar_s = bar_load + 1;   // S = Q K^T complete
     uint64_t* bar_pv = bar_load + 2;  // O += P V complete
@@ -88,10 +91,10 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
 
     if (t == 0) {
         const uint8_t* tile = a.tiles + (static_cast<size_t>(b) * a.H + h) * a.bytes_per_bh;
-        mbar_expect_tx(bar_load, (a.q_manual ? 0 : q_bytes) + 2 * a.k_tile_bytes);
+        mbar_expect_tx(bar_load, (a.q_manual ? 0 : q_bytes) + a.k_tile_bytes + a.v_tile_bytes);
         if (!a.q_manual) tma_load_4d(sQ, &tmQ, 0, m0, h * (a.d / 8), b, bar_load);
         tma_load_1d(sK, tile, a.k_tile_bytes, bar_load);
-        tma_load_1d(sV, tile + a.k_tile_bytes, a.k_tile_bytes, bar_load);
+        tma_load_1d(sV, tile + a.k_tile_bytes, a.v_tile_bytes, bar_load);
     }
     if (a.q_manual) {
         const int srow_q = m0 + t;
@@ -151,7 +154,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
             for (int c = 0; c < nchunks; ++c) {
                 const int n0 = c * CHUNK;
                 const int N = min(CHUNK, Lseg_pad - n0);
-                if (t == 0) issue_s(n0, N);
+                if (warp == 0 && elect_one()) issue_s(n0, N);
                 mbar_wait(bar_s, s_phase);
                 s_phase ^= 1;
                 tc_fence_after();
@@ -166,7 +169,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
             const int n0 = c * CHUNK;
             const int N = min(CHUNK, Lseg_pad - n0);
             const int valid = min(N, Lseg - n0);
-            if (t == 0) issue_s(n0, N);
+            if (warp == 0 && elect_one()) issue_s(n0, N);
             mbar_wait(bar_s, s_phase);
             s_phase ^= 1;
             tc_fence_after();
@@ -199,7 +202,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
             __syncthreads();
-            if (t == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc_f16(a.fmt, 128, a.d_pad);
                 for (int kk = 0; kk < N / 16; ++kk) {
@@ -252,27 +255,34 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
 // ---- context-cache packing ---------------------------------------------------------------------
 // K tile  (B operand of S = Q K^T, N = L_pad rows, K = d_pad):   [d_pad/8][L_pad][8]
 // V^T tile (B operand of O = P V,  N = d_pad rows, K = L_pad):   [L_pad/8][d_pad][8]
+// extended V^T tile (N = dv_pad rows):                           [L_pad/8][dv_pad][8]; row d_pad is all ones, rows above it zero
 // Text tokens occupy KV columns [0, Lt), audio tokens [Lt_pad, Lt_pad + La); everything else is zero.
 __global__ void kv_pack_kernel(const uint16_t* __restrict__ Kt, const uint16_t* __restrict__ Vt,
                                const uint16_t* __restrict__ Ka, const uint16_t* __restrict__ Va,
-                               uint16_t* __restrict__ tiles, KvPackGeom g, int Bc) {
+                               uint16_t* __restrict__ tiles, KvPackGeom g, int Bc, uint16_t one) {
     const int L = g.Lt + g.La;
-    const size_t per_tile = static_cast<size_t>(g.d_pad) * g.L_pad;
-    const size_t total = static_cast<size_t>(Bc) * g.H * 2 * per_tile;
+    const size_t k_elems = static_cast<size_t>(g.d_pad) * g.L_pad, vx_elems = static_cast<size_t>(g.dv_pad) * g.L_pad;
+    const size_t per_bh = 2 * k_elems + vx_elems;
+    const size_t total = static_cast<size_t>(Bc) * g.H * per_bh;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        size_t r = idx;
-        const int e = r % 8; r /= 8;
-        const bool is_v = (r / (per_tile / 8)) & 1;
-        const size_t in_tile = r % (per_tile / 8);
-        const size_t bh = r / (per_tile / 8) / 2;
+        const size_t bh = idx / per_bh;
+        size_t r = idx % per_bh;
+        const bool is_v = r >= k_elems;                 // V^T or extended V^T
+        const bool is_x = r >= 2 * k_elems;             // extended V^T
+        const int vrows = is_x ? g.dv_pad : g.d_pad;
+        if (is_x) r -= 2 * k_elems; else if (is_v) r -= k_elems;
+        const int e = r % 8;
+        const size_t in_tile = r / 8;
         const int hh = bh % g.H;
         const int bb = bh / g.H;
         int l, dim;  // KV column (padded index space) and head dimension
         if (!is_v) { dim = (in_tile / g.L_pad) * 8 + e; l = in_tile % g.L_pad; }
-        else       { l = (in_tile / g.d_pad) * 8 + e; dim = in_tile % g.d_pad; }
+        else       { l = (in_tile / vrows) * 8 + e; dim = in_tile % vrows; }
         uint16_t v = 0;
-        if (dim < g.d) {
+        if (is_v && dim == g.d_pad) {
+            v = one;
+        } else if (dim < g.d) {
             const int col = hh * g.d + dim;
             if (l < g.Lt) {
                 const uint16_t* src = is_v ? Vt : Kt;  // [Bc, L, C]; text rows come from the to_k/to_v product
@@ -290,13 +300,13 @@ __global__ void kv_pack_kernel(const uint16_t* __restrict__ Kt, const uint16_t* 
 
 int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void* cache, int Bc, int Lt, int La,
             int C, int H, int dtype, cudaStream_t st) {
-    (void)dtype;
     const KvPackGeom g = kv_pack_geom(Lt, La, C, H);
     const size_t total = static_cast<size_t>(Bc) * H * g.bytes_per_bh / 2;
     const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8));
+    const uint16_t one = dtype == APX_F16 ? 0x3C00 : 0x3F80;   // 1.0 in fp16 / bf16
     kv_pack_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(Kt), static_cast<const uint16_t*>(Vt),
                                            static_cast<const uint16_t*>(Ka), static_cast<const uint16_t*>(Va),
-                                           static_cast<uint16_t*>(cache), g, Bc);
+                                           static_cast<uint16_t*>(cache), g, Bc, one);
     APX_LAUNCH_CHECK("kv_pack_kernel");
     return APX_OK;
 }
@@ -309,7 +319,7 @@ int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int 
     APX_REQUIRE(g.d % 8 == 0 && g.d_pad <= 80, APX_EUNSUPPORTED, "ipattn_core: head dim %d (need d %% 8 == 0, d <= 80)",
                 g.d);
     APX_REQUIRE(Lt + La > 0, APX_EINVAL, "ipattn_core: empty context");
-    const size_t smem = 128 + 128u * g.d_pad * 2 + 2 * g.k_tile_bytes + 128 * CHUNK * 2 + 64;
+    const size_t smem = 128 + 128u * g.d_pad * 2 + g.k_tile_bytes + g.v_tile_bytes + 128 * CHUNK * 2 + 64;
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "ipattn_core: context of %d+%d tokens needs %zu B of shared memory",
                 Lt, La, smem);
 
@@ -331,6 +341,8 @@ int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int 
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(g.d));
     a.fmt = dtype == APX_F16 ? 0 : 1;
     a.k_tile_bytes = static_cast<uint32_t>(g.k_tile_bytes);
+    a.v_tile_bytes = static_cast<uint32_t>(g.v_tile_bytes);
+    a.dv_pad = g.dv_pad;
     a.bytes_per_bh = static_cast<uint32_t>(g.bytes_per_bh);
     a.Q = static_cast<const uint16_t*>(Q);
     static const int q_manual = [] { const char* e = getenv("APX_Q_STAGE"); return e && !strcmp(e, "manual") ? 1 : 0; }();

@@ -75,7 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: the TMA / MMA operands stay in uniform registers (no per-instruction R2UR waterfall)
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -86,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(g.in_fmt, BM, BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;

@@ -47,9 +47,12 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
             cudaStream_t st);
 
 // Packed per-(batch, head) K / V^T tiles in UMMA no-swizzle K-major core-matrix order.
+// Per (batch, head) the cache holds three tiles: K, V^T, and V^T extended by 16 rows of which the first (row d_pad) is all ones
+// (dv_pad = d_pad + 16 rows): with it P·[V | 1] also yields the softmax denominator of every row in accumulator column d_pad.
+// The first-generation kernels read {K, V^T}, the site kernel {K, extended V^T}.
 struct KvPackGeom {
-    int Lt, La, Lt_pad, La_pad, L_pad, d, d_pad, H, C;
-    size_t k_tile_bytes, v_tile_bytes, bytes_per_bh;
+    int Lt, La, Lt_pad, La_pad, L_pad, d, d_pad, dv_pad, H, C;
+    size_t k_tile_bytes, v_tile_bytes, vx_tile_bytes, bytes_per_bh;
 };
 KvPackGeom kv_pack_geom(int Lt, int La, int C, int H);
 
@@ -58,17 +61,16 @@ int ipattn_core_tc(const void* Q, const void* cache, void* O, int Bc, int S, int
 int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void* cache, int Bc, int Lt, int La,
             int C, int H, int dtype, cudaStream_t st);
 
-// ---- fused adapter site (apx_ipattn_fused.cu) ----------------------------------------------------------
-// Geometry of the pre-packed Wq / Wo blob consumed by the fused kernel; nsplit == 0 means "not covered".
-struct FusedGeom {
-    int C, H, d, d_pad, nsplit, CN;
-    size_t wq_chunk_bytes, wq_head_bytes, wo_tile_bytes, wq_off, wo_off, total;
+// ---- adapter site in one kernel (apx_ipattn_site.cu): all-head projections + two softmax warpgroups ---------------
+struct SiteGeom {
+    int ok, C, H, d, d_pad, Nq, n_kb;
+    size_t wq_chunk_bytes, wo_kstep_bytes, wq_bytes, wo_bytes, total;
 };
-FusedGeom fused_geom(int C, int H);
-bool ipattn_fused_supported(int C, int H, int Lt, int La);
-int ipattn_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
-int ipattn_fused(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S,
-                 int C, int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st);
+SiteGeom site_geom(int C, int H);
+bool ipattn_site_supported(int C, int H, int Lt, int La);
+int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
+int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
+                int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st);
 
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,

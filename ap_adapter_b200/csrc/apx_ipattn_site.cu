@@ -1,0 +1,767 @@
+// apx_ipattn_site.cu — one adapter site in ONE tcgen05 kernel, second generation ("site kernel"):
+//
+//   Y = ( softmax(Q K_t^T / sqrt(d)) V_t + ap_scale * softmax(Q K_a^T / sqrt(d)) V_a ) Wo^T + bo,   Q = X Wq^T
+//
+// (to_q, both SDPAs, the ap_scale add and to_out of APadapter/ap_adapter/attention_processor.py:387-459.)
+//
+// What the first fused kernel (apx_ipattn_fused.cu) taught us on the B200 (profiles/r1_fused_v2_trace_*.txt): with one
+// head at a time the kernel is a 7 k-cycle latency chain per head, a tcgen05.mma costs ~57 cycles to ISSUE whatever its
+// N, so N = d = 32 projections are issue-bound, and a row-per-thread global epilogue costs 5.7 k cycles.  Hence:
+//
+//   phase A   Q for ALL heads at once:  Q[128, H*d_pad] = X[128, C] · Wq^T   as N = H*d_pad wide MMAs (tensor-bound),
+//             X chunks (SWIZZLE_128B tensor TMA) and packed Wq chunks (1-D bulk TMA) through a 2-stage mbarrier ring;
+//             both warpgroups convert the fp32 accumulator to the 16-bit K-major operand tile sQO (all heads side by side).
+//   phase B   heads alternate between two softmax warpgroups (WG0: 0,2,4.. WG1: 1,3,5..), each with its own S / O_t / O_a
+//             accumulators in tensor memory and its own P tile in shared memory.  The single MMA thread keeps
+//             S(h+2) = Q_h+2 K^T and O(h) = P V in flight while the other warpgroup is in its exp2 pass, so the MUFU
+//             pipe — the real bound of this kernel at d = 32 (one ex2 per score, 16/clk/SM) — stays busy.
+//             O_h = O_t / l_t + ap_scale · O_a / l_a is formed in registers and written over Q_h in sQO.
+//   phase C   Y[128, C] = O[128, H*d_pad] · Wo^T as C-wide MMAs over the gathered O tile (Wo chunks stream through the
+//             shared memory the P tiles occupied), + bias, 16-bit, swizzled staging tile, tensor-TMA store (rows past S clipped).
+//
+// Warp roles (384 threads): warps 0-3 = WG0, warps 4-7 = WG1 (TMEM lane quarter = warp % 4), warp 8 = TMEM allocator +
+// single-thread MMA issuer (elect.sync, so that the descriptors stay in uniform registers), warp 9 = TMA producer,
+// warps 10-11 idle (they only complete the third warpgroup so that setmaxnreg can move its registers to the other two).
+#include "apx_internal.h"
+#include "apx_ptx.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace apx {
+
+SiteGeom site_geom(int C, int H) {
+    SiteGeom g;
+    memset(&g, 0, sizeof(g));
+    if (C <= 0 || H <= 0 || C % H || C % 64 || C > 256) return g;
+    const int d = C / H;
+    if (d % 8) return g;
+    const int d_pad = (d + 15) / 16 * 16;
+    const int Nq = H * d_pad;
+    if (Nq > 256) return g;
+    g.ok = 1; g.C = C; g.H = H; g.d = d; g.d_pad = d_pad; g.Nq = Nq;
+    g.n_kb = C / 64;
+    g.wq_chunk_bytes = static_cast<size_t>(Nq) * 128;            // [8 k-groups][Nq rows][8] x 2 B
+    g.wo_kstep_bytes = static_cast<size_t>(C) * 32;              // [2 k-groups][C rows][8] x 2 B
+    g.wq_bytes = g.wq_chunk_bytes * g.n_kb;
+    g.wo_bytes = g.wo_kstep_bytes * (Nq / 16);
+    g.total = g.wq_bytes + g.wo_bytes;
+    return g;
+}
+
+namespace {
+
+constexpr int X_CHUNK_BYTES = 128 * 64 * 2;   // one SWIZZLE_128B box: 128 rows x 64 channels
+constexpr int WO_KSTEPS_PER_STAGE = 4;
+constexpr int NTHREADS = 384;          // 3 warpgroups: two softmax warpgroups + {MMA warp, TMA warp, two idle warps}
+constexpr int REGS_WG = 216;           // setmaxnreg: the softmax warpgroups keep a 144-column score row in registers,
+constexpr int REGS_AUX = 72;           // the single-thread roles give their registers up (registers freed: (168-72)*128 = registers claimed: (216-168)*256)
+
+// WQ section: [C/64][8][Nq][8]: element (chunk kb, k-group kg, row n, e) = Wq[h*d + j, kb*64 + kg*8 + e], n = h*d_pad + j
+//             (rows with j >= d are zero).
+// WO section: [Nq/8][C][8]:     element (k-group kg, column n, e) = Wo[n, h*d + j], kg*8 + e = h*d_pad + j (zero for j >= d).
+__global__ void site_pack_kernel(const uint16_t* __restrict__ Wq, const uint16_t* __restrict__ Wo,
+                                 uint16_t* __restrict__ wq_out, uint16_t* __restrict__ wo_out, SiteGeom g) {
+    const size_t n_wq = g.wq_bytes / 2, n_wo = g.wo_bytes / 2;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_wq + n_wo;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        if (idx < n_wq) {
+            size_t r = idx;
+            const int e = r % 8; r /= 8;
+            const int n = r % g.Nq; r /= g.Nq;
+            const int kg = r % 8;
+            const int kb = r / 8;
+            const int h = n / g.d_pad, j = n % g.d_pad;
+            const int k = kb * 64 + kg * 8 + e;
+            wq_out[idx] = j < g.d ? Wq[static_cast<size_t>(h * g.d + j) * g.C + k] : uint16_t(0);
+        } else {
+            size_t r = idx - n_wq;
+            const int e = r % 8; r /= 8;
+            const int n = r % g.C;
+            const int kg = r / g.C;
+            const int kk = kg * 8 + e;
+            const int h = kk / g.d_pad, j = kk % g.d_pad;
+            wo_out[idx - n_wq] = j < g.d ? Wo[static_cast<size_t>(n) * g.C + h * g.d + j] : uint16_t(0);
+        }
+    }
+}
+
+struct SiteArgs {
+    const uint8_t* wq;     // packed WQ section
+    const uint8_t* wo;     // packed WO section
+    const uint8_t* tiles;  // packed context K / V^T tiles, [Bc][H]{K tile, V^T tile}
+    const float* bo;       // fp32[C] or null
+    int S, C, H, d_pad, dv_pad, Nq, n_kb;
+    int Lt, La, Lt_pad, La_pad, L_pad;
+    float ap_scale, scale_log2;
+    uint32_t kv_bytes, k_tile_bytes, v_tile_bytes, vx_off, wq_chunk_bytes, wo_kstep_bytes, a_stage_bytes, p_bytes;
+    int nk, nv, n_wo, wo_early;                // K ring, V ring depths; Wo stages / how many have their own region
+    uint32_t off_p, off_k, off_v, off_bar;     // shared-memory offsets from the 1024-aligned base (sQO is at 0)
+    uint32_t wo_off[4];                        // where each Wo stage lands
+    long long* trace;                          // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0)
+};
+
+// trace slots: [0,32) MMA thread, [32,64) producer, [64,192) WG0 thread 0 (8 per head), [192,320) WG1 thread 128
+#define SITE_T(slot)                                                                             \
+    do {                                                                                         \
+        if (TRACE && a.trace && blockIdx.x == 0 && blockIdx.y == 0) a.trace[(slot)] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+
+// tcgen05.mma with the descriptors given as (lo, hi) words: along a K chain only the 14-bit start-address field in the low
+// word moves (every operand lives below 256 KB, so it cannot carry out), which keeps the per-MMA issue cost at two 32-bit
+// uniform adds.
+__device__ __forceinline__ void umma_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// n dependent tcgen05.mma steps along K: A advances by a_step bytes, B by b_step bytes per 16-element k-step.
+__device__ __forceinline__ void mma_chain(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t a_step, uint32_t b_step, int n,
+                                          uint32_t idesc, uint32_t acc_first) {
+    uint32_t a_lo = static_cast<uint32_t>(da), b_lo = static_cast<uint32_t>(db);
+    const uint32_t a_hi = static_cast<uint32_t>(da >> 32), b_hi = static_cast<uint32_t>(db >> 32);
+    a_step >>= 4; b_step >>= 4;
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        umma_ss_lohi(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, acc_first | static_cast<uint32_t>(k));
+        a_lo += a_step;
+        b_lo += b_step;
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void store16(uint32_t dst, const float* v) {   // 16 values -> two 16-byte core-matrix rows
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack2<FMT>(v[2 * i], v[2 * i + 1]);
+    st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+    st_shared_v4(dst + 2048, w[4], w[5], w[6], w[7]);
+}
+
+// Orders every later use of r[0..16) after this point (placed after tcgen05.wait::ld; emits no instruction).
+__device__ __forceinline__ void reg_tie16(uint32_t* r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ float max16(const uint32_t* r) {
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+    return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+__device__ __forceinline__ void mask16(uint32_t* r, int nv) {   // columns >= nv of the group -> -inf (exp2 -> exactly 0)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = i < nv ? r[i] : 0xff800000u;
+}
+// exp2(r * sl - mxs) of a 16-column group -> 16 bit -> two core-matrix rows of the P tile (unnormalised: the row sums come
+// out of the tensor core, from the ones row of the V^T tile)
+template <int FMT>
+__device__ __forceinline__ void exp_store16(const uint32_t* r, float sl, float mxs, uint32_t dst) {
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl, -mxs));
+    store16<FMT>(dst, e);
+}
+template <int FMT>
+__device__ __forceinline__ void cvt_store16(const uint32_t* r, uint32_t dst) {   // fp32 accumulator group -> 16 bit -> two core-matrix rows
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    store16<FMT>(dst, v);
+}
+
+enum {  // mbarrier slots (40 x 8 bytes reserved; the TMEM slot and the bias slice follow)
+    B_A_FULL = 0, B_K_FULL = 4, B_K_EMPTY = 7, B_V_FULL = 10, B_V_EMPTY = 13, B_WO_FULL = 16, B_Q = 20, B_SQ = 21, B_S_FULL = 22,
+    B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_COUNT = 33
+};
+constexpr uint32_t BAR_REGION_BYTES = 384;   // barriers [0, 320) | TMEM slot at 320 | bias slice from 384
+
+// N16 > 0: the score row is N16 16-column groups, the first LT16 of them text, and it is read from tensor memory ONCE and kept
+//          in registers for both softmax passes (the score buffer is handed back to the MMA thread right after the load).
+// N16 == 0: any context shape; two passes over tensor memory (maxima, exponentials).
+// The code is kept compact on purpose: the SM's instruction cache holds 32 KB, and code that falls out of it runs at ~10 cycles
+// per instruction (measured: profiles/r1_site_v3_trace_*.txt).
+template <int FMT, int N16, int LT16, bool TRACE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, SiteArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQO = smem;                 // [Nq/8][128][8] 16 bit: Q of every head, overwritten head by head with O; then Y staging
+    uint8_t* sP = smem + a.off_p;        // P tiles of the two warpgroups
+    uint8_t* sK = smem + a.off_k;        // K tile ring
+    uint8_t* sV = smem + a.off_v;        // V^T tile ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.off_bar + 320);
+    float* sBias = reinterpret_cast<float*>(smem + a.off_bar + BAR_REGION_BYTES);
+    // phase A stages (X chunk + Wq chunk, one per 64 input channels) lie over everything below the barriers: nothing else
+    // is live until the Q accumulator is complete.
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128;
+    const int b = blockIdx.y;
+
+    if (threadIdx.x == 288) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmY);
+#pragma unroll 1
+        for (int i = 0; i < B_COUNT; ++i) {
+            const uint32_t cnt = (i == B_SQ || i == B_SO_ALL) ? 256u : (i >= B_S_FREE && i < B_O_FULL) ? 128u : 1u;
+            mbar_init(&bars[i], cnt);   // warpgroup -> MMA barriers count every arriving thread
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (threadIdx.x < 256) {
+        for (int i = threadIdx.x; i < a.C; i += 256) sBias[i] = a.bo ? a.bo[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // phase A: Q at [0, Nq).  phase B: S(g) at g * L_pad, then {O_t(g), O_a(g)}, dv_pad columns each (column d_pad = row sum).
+    // phase C: Y at [0, C).
+    const uint32_t tmem_O = tmem_base + 2 * a.L_pad;
+    const int n_ko = a.Nq / 16;   // k-steps of the out-projection
+
+    if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+    if (warp == 9) {
+        // ================================================================ TMA producer (one thread)
+        if (elect_one()) {
+            SITE_T(32);
+#pragma unroll 1
+            for (int kb = 0; kb < a.n_kb; ++kb) {   // every phase-A chunk has a stage of its own: all loads are in flight at once
+                uint8_t* dst = smem + kb * a.a_stage_bytes;
+                mbar_expect_tx(&bars[B_A_FULL + kb], X_CHUNK_BYTES + a.wq_chunk_bytes);
+                tma_load_3d(dst, &tmX, kb * 64, m0, b, &bars[B_A_FULL + kb]);
+                tma_load_1d(dst + X_CHUNK_BYTES, a.wq + static_cast<size_t>(kb) * a.wq_chunk_bytes, a.wq_chunk_bytes,
+                            &bars[B_A_FULL + kb]);
+            }
+            mbar_wait_nocall(&bars[B_Q], 0);   // the Q accumulator is complete: the phase-A stages are dead
+            SITE_T(33);
+            const uint8_t* kv_src = a.tiles + static_cast<size_t>(b) * a.H * a.kv_bytes;
+            auto load_wo = [&](int w) {
+                const int ks = min(WO_KSTEPS_PER_STAGE, n_ko - w * WO_KSTEPS_PER_STAGE);
+                mbar_expect_tx(&bars[B_WO_FULL + w], ks * a.wo_kstep_bytes);
+                tma_load_1d(smem + a.wo_off[w], a.wo + static_cast<size_t>(w) * WO_KSTEPS_PER_STAGE * a.wo_kstep_bytes,
+                            ks * a.wo_kstep_bytes, &bars[B_WO_FULL + w]);
+            };
+            // Issue order = the MMA thread's consumption order: K(2p), K(2p+1), then V(2p), V(2p+1) (a different order can
+            // deadlock: the ring waits of one tile kind would sit in front of a tile the MMA thread needs first).
+            int sk = 0, sv = 0;               // ring slots of the next K / V^T tile
+            uint32_t pk = 1, pv = 1;          // "empty" parities of those slots (first pass: free)
+#pragma unroll 1
+            for (int h0 = 0; h0 < a.H; h0 += 2) {
+#pragma unroll 1
+                for (int h = h0; h < h0 + 2 && h < a.H; ++h) {
+                    mbar_wait_nocall(&bars[B_K_EMPTY + sk], pk);
+                    mbar_expect_tx(&bars[B_K_FULL + sk], a.k_tile_bytes);
+                    tma_load_1d(sK + sk * a.k_tile_bytes, kv_src + static_cast<size_t>(h) * a.kv_bytes, a.k_tile_bytes, &bars[B_K_FULL + sk]);
+                    if (++sk == a.nk) { sk = 0; pk ^= 1; }
+                }
+#pragma unroll 1
+                for (int h = h0; h < h0 + 2 && h < a.H; ++h) {
+                    mbar_wait_nocall(&bars[B_V_EMPTY + sv], pv);
+                    mbar_expect_tx(&bars[B_V_FULL + sv], a.v_tile_bytes);
+                    tma_load_1d(sV + sv * a.v_tile_bytes, kv_src + static_cast<size_t>(h) * a.kv_bytes + a.vx_off, a.v_tile_bytes,
+                                &bars[B_V_FULL + sv]);
+                    if (++sv == a.nv) { sv = 0; pv ^= 1; }
+                }
+                if (h0 == 0) {                // the early Wo stage(s) go out behind the first pair of tiles
+#pragma unroll 1
+                    for (int w = 0; w < a.wo_early; ++w) load_wo(w);
+                }
+            }
+            SITE_T(34);
+            mbar_wait_nocall(&bars[B_PV_ALL], 0);   // the P tiles and the K / V rings are dead once every P·V has completed
+            SITE_T(35);
+#pragma unroll 1
+            for (int w = a.wo_early; w < a.n_wo; ++w) load_wo(w);
+            SITE_T(36);
+        }
+    } else if (warp == 8) {
+        // ================================================================ MMA issuer (one thread)
+        if (elect_one()) {
+            const uint32_t idesc_q = umma_idesc_f16(FMT, 128, a.Nq);
+            const uint32_t idesc_s = umma_idesc_f16(FMT, 128, a.L_pad);
+            const uint32_t idesc_y = umma_idesc_f16(FMT, 128, a.C);
+            // ---- phase A: Q = X · Wq^T, all heads
+            SITE_T(0);
+#pragma unroll 1
+            for (int kb = 0; kb < a.n_kb; ++kb) {
+                mbar_wait_nocall(&bars[B_A_FULL + kb], 0);
+                tc_fence_after();
+                if (kb == 0) SITE_T(1);
+                const uint32_t base = smem_u32(smem + kb * a.a_stage_bytes);
+                mma_chain(tmem_base, umma_desc(base, 16, 1024, kLayoutSW128),
+                          umma_desc(base + X_CHUNK_BYTES, a.Nq * 16, 128, kLayoutNone), 32, 2 * a.Nq * 16, 4, idesc_q,
+                          static_cast<uint32_t>(kb));
+            }
+            umma_commit(&bars[B_Q]);
+            SITE_T(2);
+            // ---- phase B.  Per pair of heads (one per warpgroup): as soon as a warpgroup has moved its score row to registers
+            //      (S_FREE) the scores of its NEXT head are issued, so they are complete long before it needs them; P·V of a head
+            //      is issued when its P tile is ready (P_FULL) and runs under the other warpgroup's / the next head's softmax.
+            const uint64_t dQO = umma_desc(smem_u32(sQO), 2048, 128, kLayoutNone);
+            const uint32_t head_bytes = (a.d_pad / 8) * 2048;   // one head's slice of sQO
+            const uint32_t idesc_v = umma_idesc_f16(FMT, 128, a.dv_pad);
+            const uint64_t dP0 = umma_desc(smem_u32(sP), 2048, 128, kLayoutNone);
+            const uint64_t dK0 = umma_desc(smem_u32(sK), a.L_pad * 16, 128, kLayoutNone);
+            const uint64_t dV0 = umma_desc(smem_u32(sV), a.dv_pad * 16, 128, kLayoutNone);
+            int sk = 0, sv = 0;               // K ring slot of the next S; V ring slot of the next P·V
+            uint32_t pk = 0, pv = 0;          // "full" parities of those ring slots
+            mbar_wait_nocall(&bars[B_SQ], 0);   // every Q column is in sQO; the Q accumulator columns are free
+            tc_fence_after();
+            SITE_T(3);
+            const int n_pairs = (a.H + 1) / 2;
+#pragma unroll 1
+            for (int p = 0; p <= n_pairs; ++p) {
+                const uint32_t par = (p - 1) & 1;
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {   // scores of heads 2p, 2p+1
+                    const int h = 2 * p + g;
+                    if (h >= a.H) break;
+                    if (p > 0) {   // S(h - 2) is in registers: its buffer is free
+                        mbar_wait_nocall(&bars[B_S_FREE + g], par);
+                        tc_fence_after();
+                    }
+                    mbar_wait_nocall(&bars[B_K_FULL + sk], pk);
+                    tc_fence_after();
+                    mma_chain(tmem_base + g * a.L_pad, desc_add(dQO, h * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048,
+                              2 * a.L_pad * 16, a.d_pad / 16, idesc_s, 0);
+                    umma_commit(&bars[B_S_FULL + g]);
+                    umma_commit(&bars[B_K_EMPTY + sk]);
+                    if (++sk == a.nk) { sk = 0; pk ^= 1; }
+                }
+                if (p == 0) continue;
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {   // P·V of heads 2p-2, 2p-1
+                    const int h = 2 * (p - 1) + g;
+                    if (h >= a.H) break;
+                    mbar_wait_nocall(&bars[B_P_FULL + g], par);   // P(h) is in shared memory, O(g) has been read
+                    mbar_wait_nocall(&bars[B_V_FULL + sv], pv);
+                    tc_fence_after();
+                    if (h < 8) SITE_T(8 + 2 * h);
+                    const uint64_t dP = desc_add(dP0, g * a.p_bytes), dV = desc_add(dV0, sv * a.v_tile_bytes);
+                    const uint32_t tO = tmem_O + g * 2 * a.dv_pad;
+                    // text columns [0, Lt_pad) -> O_t, audio columns [Lt_pad, L_pad) -> O_a
+                    mma_chain(tO, dP, dV, 2 * 2048, 2 * a.dv_pad * 16, a.Lt_pad / 16, idesc_v, 0);
+                    mma_chain(tO + a.dv_pad, desc_add(dP, (a.Lt_pad / 8) * 2048), desc_add(dV, (a.Lt_pad / 8) * (a.dv_pad * 16)),
+                              2 * 2048, 2 * a.dv_pad * 16, a.La_pad / 16, idesc_v, 0);
+                    umma_commit(&bars[B_O_FULL + g]);
+                    umma_commit(&bars[B_V_EMPTY + sv]);
+                    if (++sv == a.nv) { sv = 0; pv ^= 1; }
+                    if (h < 8) SITE_T(9 + 2 * h);
+                }
+            }
+            umma_commit(&bars[B_PV_ALL]);
+            // ---- phase C: Y = O · Wo^T
+            mbar_wait_nocall(&bars[B_SO_ALL], 0);   // every O_h is in sQO and every accumulator has been read
+            tc_fence_after();
+            SITE_T(5);
+#pragma unroll 1
+            for (int i = 0; i < a.n_wo; ++i) {
+                const int ks = min(WO_KSTEPS_PER_STAGE, n_ko - i * WO_KSTEPS_PER_STAGE);
+                mbar_wait_nocall(&bars[B_WO_FULL + i], 0);
+                tc_fence_after();
+                if (i == 0) SITE_T(6);
+                mma_chain(tmem_base, desc_add(dQO, i * WO_KSTEPS_PER_STAGE * 2 * 2048),
+                          umma_desc(smem_u32(smem + a.wo_off[i]), a.C * 16, 128, kLayoutNone), 2 * 2048, a.wo_kstep_bytes, ks,
+                          idesc_y, static_cast<uint32_t>(i));
+            }
+            umma_commit(&bars[B_Y]);
+            SITE_T(7);
+        }
+    }
+    } else {
+        // ================================================================ the two softmax / conversion / epilogue warpgroups
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WG));
+        const int g = warp >> 2;                // warpgroup
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // tile row == TMEM lane
+        const uint32_t lane_taddr = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t sQO_row = smem_u32(sQO) + row * 16;   // element (row, c) of a K-major core-matrix tile:
+        const uint32_t sP_row = smem_u32(sP + g * a.p_bytes) + row * 16;   //   (c / 8) * 2048 + row * 16 + (c % 8) * 2
+        const float sl = a.scale_log2;
+        const int la_end = a.Lt_pad + a.La;
+        const bool t0 = lane == 0 && q == 0;    // the thread of this warpgroup that writes trace stamps
+        const int tb = 64 + g * 128;
+
+        // ---- phase A: Q accumulator -> 16-bit operand tile; the warpgroups split the 16-column groups
+        {
+            const int n16 = a.Nq / 16, half = (n16 + 1) / 2;
+            const int c_lo = g == 0 ? 0 : half, c_hi = g == 0 ? half : n16;
+            if (t0) SITE_T(tb + 120);
+            mbar_wait_nocall(&bars[B_Q], 0);
+            tc_fence_after();
+            if (t0) SITE_T(tb + 121);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {   // 8 loads per tcgen05.wait::ld: the round trip is the cost, not the bytes
+                uint32_t r[128];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < c_hi) tmem_ld16(tmem_base + lane_taddr + (c0 + j) * 16, r + j * 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < c_hi) { reg_tie16(r + j * 16); cvt_store16<FMT>(r + j * 16, sQO_row + (c0 + j) * 2 * 2048); }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&bars[B_SQ]);
+            if (t0) SITE_T(tb + 122);
+        }
+
+        // ---- phase B: this warpgroup's heads.  Order per head: score row -> registers (the buffer goes straight back to the MMA
+        //      thread), maxima, convert the O of this warpgroup's PREVIOUS head (its P·V ran meanwhile), exponentials -> P tile.
+        //      Nothing in this loop waits for work that was issued after the loop iteration began.
+        const uint32_t tO = tmem_O + lane_taddr + g * 2 * a.dv_pad;
+        const uint32_t tS = tmem_base + lane_taddr + g * a.L_pad;
+        // O_h = O_t / l_t + ap_scale * O_a / l_a -> 16 bit, over Q_h in sQO; l_t, l_a = accumulator column d_pad (ones row of V^T).
+        // A segment that does not exist reads the other accumulator with weight 0 (its own columns were never written).
+        const uint32_t tOt = a.Lt > 0 ? tO : tO + a.dv_pad, tOa = a.La > 0 ? tO + a.dv_pad : tO;
+        auto convert_o = [&](int h, uint32_t ph) {
+            mbar_wait_nocall(&bars[B_O_FULL + g], ph);
+            tc_fence_after();
+            uint32_t lt, la;
+            tmem_ld1(tOt + a.d_pad, lt);
+            tmem_ld1(tOa + a.d_pad, la);
+            float w_t = 0.f, w_a = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < a.d_pad; c0 += 32) {   // two 16-column groups of each accumulator per round trip
+                uint32_t rt[32], ra[32];
+                const bool two = c0 + 16 < a.d_pad;
+                tmem_ld16(tOt + c0, rt);
+                tmem_ld16(tOa + c0, ra);
+                if (two) { tmem_ld16(tOt + c0 + 16, rt + 16); tmem_ld16(tOa + c0 + 16, ra + 16); }
+                tmem_ld_wait();
+                if (c0 == 0) {
+                    asm volatile("" : "+r"(lt), "+r"(la) : : "memory");
+                    w_t = a.Lt > 0 ? 1.0f / __uint_as_float(lt) : 0.f;
+                    w_a = a.La > 0 ? a.ap_scale / __uint_as_float(la) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j == 0 || two) {
+                        reg_tie16(rt + j * 16);
+                        reg_tie16(ra + j * 16);
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ra[j * 16 + i]), w_a, __uint_as_float(rt[j * 16 + i]) * w_t);
+                        store16<FMT>(sQO_row + (h * a.d_pad + c0 + j * 16) / 8 * 2048, v);
+                    }
+                }
+            }
+        };
+        if (g == 1 && a.H > 1) named_bar_sync(2, 256);
+#pragma unroll 1
+        for (int it = 0;; ++it) {
+            const int h = g + 2 * it;
+            const bool live = h < a.H;
+            const int ts = tb + it * 8;
+            const bool tr = t0 && it < 15 && live;
+            float mx_t = -INFINITY, mx_a = -INFINITY;
+            uint32_t s[(N16 > 0 ? N16 : 1) * 16];
+            if (live) {
+                if (tr) SITE_T(ts + 0);
+                mbar_wait_nocall(&bars[B_S_FULL + g], it & 1);
+                tc_fence_after();
+                if (tr) SITE_T(ts + 1);
+                // two softmaxes over one score row: text columns [0, Lt), audio columns [Lt_pad, Lt_pad + La); P stays unnormalised
+                if (N16 > 0) {
+#pragma unroll
+                    for (int c = 0; c < N16; ++c) tmem_ld16(tS + c * 16, s + c * 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < N16; ++c) reg_tie16(s + c * 16);
+                    tc_fence_before();
+                    mbar_arrive(&bars[B_S_FREE + g]);   // the scores of this warpgroup's next head may be issued now
+                    if (tr) SITE_T(ts + 6);
+                    // padded columns (only the last group of a segment can have any) -> -inf
+                    if (LT16 > 0 && a.Lt < LT16 * 16) mask16(s + (LT16 > 0 ? LT16 - 1 : 0) * 16, a.Lt - (LT16 - 1) * 16);
+                    if (N16 > LT16 && la_end < N16 * 16) mask16(s + (N16 - 1) * 16, la_end - (N16 - 1) * 16);
+#pragma unroll
+                    for (int c = 0; c < N16; ++c) {
+                        if (c < LT16) mx_t = fmaxf(mx_t, max16(s + c * 16)); else mx_a = fmaxf(mx_a, max16(s + c * 16));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < a.L_pad / 16; ++c) {   // pass 1 over tensor memory: maxima
+                        uint32_t r[16];
+                        tmem_ld16(tS + c * 16, r);
+                        tmem_ld_wait16(r);
+                        const bool text = c * 16 < a.Lt_pad;
+                        mask16(r, (text ? a.Lt : la_end) - c * 16);
+                        const float m = max16(r);
+                        if (text) mx_t = fmaxf(mx_t, m); else mx_a = fmaxf(mx_a, m);
+                    }
+                }
+                if (tr) SITE_T(ts + 2);
+            }
+            // the O of this warpgroup's previous head: its P·V ran under the code above; also frees this warpgroup's P tile
+            if (it > 0) convert_o(h - 2, (it - 1) & 1);
+            if (!live) break;
+            if (tr) SITE_T(ts + 4);
+            // One-time skew: warpgroup 1 starts when warpgroup 0 enters its first exponential pass, so that from then on one
+            // warpgroup's MUFU-bound pass runs under the other's tensor-memory / conversion work instead of both in lockstep.
+            if (it == 0 && g == 0 && a.H > 1) named_bar_arrive(2, 256);
+            const float mxs_t = mx_t * sl, mxs_a = mx_a * sl;
+            if (N16 > 0) {
+#pragma unroll
+                for (int c = 0; c < N16; ++c) exp_store16<FMT>(s + c * 16, sl, c < LT16 ? mxs_t : mxs_a, sP_row + c * 2 * 2048);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < a.L_pad / 16; ++c) {   // pass 2: exponentials
+                    uint32_t r[16];
+                    tmem_ld16(tS + c * 16, r);
+                    tmem_ld_wait16(r);
+                    const bool text = c * 16 < a.Lt_pad;
+                    mask16(r, (text ? a.Lt : la_end) - c * 16);
+                    exp_store16<FMT>(r, sl, text ? mxs_t : mxs_a, sP_row + c * 2 * 2048);
+                }
+                tc_fence_before();
+                mbar_arrive(&bars[B_S_FREE + g]);
+            }
+            if (tr) SITE_T(ts + 7);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&bars[B_P_FULL + g]);
+            if (tr) SITE_T(ts + 3);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bars[B_SO_ALL]);
+
+        // ---- phase C epilogue: Y accumulator + bias -> 16 bit -> SWIZZLE_128B staging boxes (over sQO) -> TMA store
+        if (t0) SITE_T(tb + 123);
+        mbar_wait_nocall(&bars[B_Y], 0);
+        tc_fence_after();
+        if (t0) SITE_T(tb + 124);
+        {
+            // 64-column boxes alternate between the warpgroups; each box is converted by one warpgroup (4 loads, one round trip),
+            // fenced, and stored by that warpgroup's first thread while the next box is being converted.
+            const uint32_t stage_row = smem_u32(sQO) + row * 128;
+            const int sw = row & 7;
+#pragma unroll 1
+            for (int kb = g; kb < a.C / 64; kb += 2) {
+                uint32_t r[64];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tmem_ld16(tmem_base + lane_taddr + kb * 64 + j * 16, r + j * 16);
+                tmem_ld_wait();
+                const uint32_t box = stage_row + kb * X_CHUNK_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    reg_tie16(r + j * 16);
+                    uint32_t p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 bb = *reinterpret_cast<const float2*>(sBias + kb * 64 + j * 16 + 2 * i);
+                        p[i] = pack2<FMT>(__uint_as_float(r[j * 16 + 2 * i]) + bb.x, __uint_as_float(r[j * 16 + 2 * i + 1]) + bb.y);
+                    }
+                    // 16-byte chunks 2j, 2j+1 of the 128-byte row; chunk k lives at k ^ (row & 7)  (SWIZZLE_128B)
+                    st_shared_v4(box + (((2 * j) ^ sw) << 4), p[0], p[1], p[2], p[3]);
+                    st_shared_v4(box + (((2 * j + 1) ^ sw) << 4), p[4], p[5], p[6], p[7]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(3 + g, 128);
+                if (t0) {
+                    tma_store_3d(&tmY, sQO + kb * X_CHUNK_BYTES, kb * 64, m0, b);
+                    tma_store_commit();
+                }
+            }
+            if (t0) {
+                SITE_T(tb + 125);
+                tma_store_wait_read();
+                SITE_T(tb + 126);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+struct SitePlan {
+    bool ok;
+    int nk, nv, n_wo, wo_early;
+    uint32_t off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, smem_bytes, wo_off[4];
+};
+
+SitePlan site_plan(const SiteGeom& g, int Lt, int La) {
+    SitePlan p;
+    memset(&p, 0, sizeof(p));
+    if (!g.ok || Lt < 0 || La < 0 || Lt + La <= 0) return p;
+    const KvPackGeom kg = kv_pack_geom(Lt, La, g.C, g.H);
+    if (kg.L_pad < 16 || kg.L_pad > 256) return p;
+    // tensor-memory columns of phase B: S(0) S(1) | O_t O_a (0) | O_t O_a (1)
+    if (2 * kg.L_pad + 4 * kg.dv_pad > 512) return p;
+    if (g.n_kb > 4) return p;
+    const uint32_t qo_bytes = static_cast<uint32_t>(std::max(g.Nq, g.C)) * 256;   // sQO, later the Y staging boxes
+    p.a_stage_bytes = X_CHUNK_BYTES + static_cast<uint32_t>(g.wq_chunk_bytes);
+    p.p_bytes = 128u * kg.L_pad * 2;
+    const uint32_t wo_stage = WO_KSTEPS_PER_STAGE * static_cast<uint32_t>(g.wo_kstep_bytes);
+    p.n_wo = (g.Nq / 16 + WO_KSTEPS_PER_STAGE - 1) / WO_KSTEPS_PER_STAGE;
+    if (p.n_wo > 4) return p;
+    const uint32_t limit = 227u * 1024u - 1024u;   // minus the alignment slack of the dynamic shared-memory base
+    const int ring_max = std::min(3, g.H), ring_min = std::min(2, g.H);
+    for (int early = 1; early >= 0; --early)
+        for (int ring = ring_max; ring >= ring_min; --ring) {
+            uint32_t off = qo_bytes;
+            p.off_p = off; off += static_cast<uint32_t>(align_up(2 * p.p_bytes, 1024));
+            p.off_k = off; off += static_cast<uint32_t>(align_up(ring * kg.k_tile_bytes, 128));
+            p.off_v = off; off += static_cast<uint32_t>(align_up(ring * kg.vx_tile_bytes, 1024));
+            // Wo stages that are loaded after the last P·V lie over the dead P tiles and K / V rings (extended if those are small)
+            off = std::max(off, p.off_p + (p.n_wo - early) * wo_stage);
+            for (int i = early; i < p.n_wo; ++i) p.wo_off[i] = p.off_p + (i - early) * wo_stage;
+            if (early) { p.wo_off[0] = off; off += wo_stage; }   // a region of its own: prefetched right after phase A
+            off = std::max(off, static_cast<uint32_t>(g.n_kb) * p.a_stage_bytes);   // the phase-A stages overlay all of the above
+            p.off_bar = static_cast<uint32_t>(align_up(off, 128));
+            const uint32_t total = p.off_bar + BAR_REGION_BYTES + static_cast<uint32_t>(g.C) * 4;
+            if (total <= limit) {
+                p.ok = true; p.nk = ring; p.nv = ring; p.wo_early = early; p.smem_bytes = total + 1024;
+                return p;
+            }
+        }
+    return p;
+}
+
+}  // namespace
+
+bool ipattn_site_supported(int C, int H, int Lt, int La) {
+    const SiteGeom g = site_geom(C, H);
+    return g.ok && site_plan(g, Lt, La).ok;
+}
+
+int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st) {
+    const SiteGeom g = site_geom(C, H);
+    APX_REQUIRE(g.ok, APX_EUNSUPPORTED, "ipattn_site_pack: the site kernel does not cover C=%d H=%d", C, H);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site_pack: dtype %d", dtype);
+    const size_t total = g.total / 2;
+    const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8));
+    uint8_t* pb = static_cast<uint8_t*>(pack);
+    site_pack_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(Wq), static_cast<const uint16_t*>(Wo),
+                                             reinterpret_cast<uint16_t*>(pb), reinterpret_cast<uint16_t*>(pb + g.wq_bytes), g);
+    APX_LAUNCH_CHECK("site_pack_kernel");
+    return APX_OK;
+}
+
+int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
+                int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st) {
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site: dtype %d", dtype);
+    const SiteGeom g = site_geom(C, H);
+    APX_REQUIRE(g.ok, APX_EUNSUPPORTED, "ipattn_site: C=%d H=%d is not covered", C, H);
+    const SitePlan p = site_plan(g, Lt, La);
+    APX_REQUIRE(p.ok, APX_EUNSUPPORTED, "ipattn_site: context %d+%d does not fit the site kernel at C=%d", Lt, La, C);
+    APX_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(wpack) & 15) == 0 && (reinterpret_cast<uintptr_t>(cache_tiles) & 15) == 0,
+                APX_EINVAL, "ipattn_site: X / Y / pack / cache must be 16-byte aligned");
+    APX_REQUIRE(Bc <= 65535, APX_EUNSUPPORTED, "ipattn_site: Bc=%d", Bc);
+    const KvPackGeom kg = kv_pack_geom(Lt, La, C, H);
+
+    CUtensorMap tmX, tmY;
+    {
+        // [Bc][S][C] viewed as a 3-D tensor so that the rows of a tile past S are zero-filled (load) / clipped (store)
+        uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(S), static_cast<uint64_t>(Bc)};
+        uint64_t strides[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(S) * C * 2};
+        uint32_t box[3] = {64, 128, 1};
+        int rc = encode_tmap(&tmX, dtype, 3, X, dims, strides, box, 1);
+        if (rc) return rc;
+        rc = encode_tmap(&tmY, dtype, 3, Y, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    SiteArgs a;
+    const uint8_t* pb = static_cast<const uint8_t*>(wpack);
+    a.wq = pb;
+    a.wo = pb + g.wq_bytes;
+    a.tiles = static_cast<const uint8_t*>(cache_tiles);
+    a.bo = bo;
+    a.S = S; a.C = C; a.H = H; a.d_pad = g.d_pad; a.dv_pad = kg.dv_pad; a.Nq = g.Nq; a.n_kb = g.n_kb;
+    a.Lt = Lt; a.La = La; a.Lt_pad = kg.Lt_pad; a.La_pad = kg.La_pad; a.L_pad = kg.L_pad;
+    a.ap_scale = ap_scale;
+    a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(g.d));
+    a.kv_bytes = static_cast<uint32_t>(kg.bytes_per_bh);
+    a.k_tile_bytes = static_cast<uint32_t>(kg.k_tile_bytes);
+    a.v_tile_bytes = static_cast<uint32_t>(kg.vx_tile_bytes);   // the site kernel streams the EXTENDED V^T tile
+    a.vx_off = static_cast<uint32_t>(kg.k_tile_bytes + kg.v_tile_bytes);
+    a.wq_chunk_bytes = static_cast<uint32_t>(g.wq_chunk_bytes);
+    a.wo_kstep_bytes = static_cast<uint32_t>(g.wo_kstep_bytes);
+    a.a_stage_bytes = p.a_stage_bytes;
+    a.p_bytes = p.p_bytes;
+    a.nk = p.nk; a.nv = p.nv; a.n_wo = p.n_wo; a.wo_early = p.wo_early;
+    a.off_p = p.off_p; a.off_k = p.off_k; a.off_v = p.off_v; a.off_bar = p.off_bar;
+    for (int i = 0; i < 4; ++i) a.wo_off[i] = p.wo_off[i];
+
+    // diagnostic timeline (APX_SITE_TRACE=1): synchronises and prints, never enabled on the product path
+    static const bool trace_on = [] { const char* e = getenv("APX_SITE_TRACE"); return e && e[0] == '1'; }();
+    static long long* trace_buf = nullptr;
+    a.trace = nullptr;
+    if (trace_on) {
+        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 320 * sizeof(long long)));
+        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 320 * sizeof(long long), st));
+        a.trace = trace_buf;
+    }
+    // kernel variant: score rows of 32 / 48 / 144 columns (La = 8 / 32 / 128 behind 1..16 text tokens) stay in registers
+    const int n16 = kg.L_pad / 16;
+    const int variant = kg.Lt_pad != 16 ? 0 : n16 == 2 ? 1 : n16 == 3 ? 2 : n16 == 9 ? 3 : 0;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, SiteArgs);
+    static const KernelFn table[3][4] = {
+        {ipattn_site_kernel<0, 0, 0, false>, ipattn_site_kernel<0, 2, 1, false>, ipattn_site_kernel<0, 3, 1, false>, ipattn_site_kernel<0, 9, 1, false>},
+        {ipattn_site_kernel<1, 0, 0, false>, ipattn_site_kernel<1, 2, 1, false>, ipattn_site_kernel<1, 3, 1, false>, ipattn_site_kernel<1, 9, 1, false>},
+        {ipattn_site_kernel<0, 0, 0, true>, ipattn_site_kernel<0, 2, 1, true>, ipattn_site_kernel<0, 3, 1, true>, ipattn_site_kernel<0, 9, 1, true>}};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 4; ++j)
+                APX_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(table[i][j]), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(S, 128), Bc);
+    const KernelFn fn = table[(trace_on && dtype == APX_F16) ? 2 : (dtype == APX_F16 ? 0 : 1)][variant];
+    fn<<<grid, NTHREADS, p.smem_bytes, st>>>(tmX, tmY, a);
+    APX_LAUNCH_CHECK("ipattn_site_kernel");
+    if (trace_on) {
+        static int printed = 0;
+        long long t[320];
+        APX_CUDA(cudaStreamSynchronize(st));
+        APX_CUDA(cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost));
+        if (printed++ < 2) {
+            const long long t0 = t[0];
+            auto rel = [&](int slot) { return t[slot] ? t[slot] - t0 : -1; };
+            printf("[apx site trace] Bc=%d S=%d C=%d H=%d Lt=%d La=%d ring=%d n_wo=%d (cycles since the MMA thread started; CTA 0)\n", Bc, S, C, H,
+                   Lt, La, p.nk, p.n_wo);
+            printf("  mma : a_full0 %lld q_committed %lld sq_seen %lld (unused %lld) | so_all_seen %lld wo_full0 %lld y_committed %lld\n",
+                   rel(1), rel(2), rel(3), rel(4), rel(5), rel(6), rel(7));
+            for (int h = 0; h < H && h < 8; ++h) printf("  mma h%d: p_full_seen %lld issued %lld\n", h, rel(8 + 2 * h), rel(9 + 2 * h));
+            printf("  tma : start %lld q_done_seen %lld kv_all_issued %lld pv_all_seen %lld wo_issued %lld\n", rel(32), rel(33), rel(34),
+                   rel(35), rel(36));
+            for (int g = 0; g < 2; ++g) {
+                const int o = 64 + g * 128;
+                printf("  wg%d : q_wait %lld q_seen %lld sq_arrived %lld | y_wait %lld y_seen %lld staged %lld stored %lld\n", g, rel(o + 120),
+                       rel(o + 121), rel(o + 122), rel(o + 123), rel(o + 124), rel(o + 125), rel(o + 126));
+                for (int i = 0; g + 2 * i < H && i < 15; ++i)
+                    printf("  wg%d h%d: top %lld s_seen %lld ld_done %lld max_done %lld oprev_done %lld exp_done %lld p_arrived %lld (unused %lld)\n", g,
+                           g + 2 * i, rel(o + i * 8), rel(o + i * 8 + 1), rel(o + i * 8 + 6), rel(o + i * 8 + 2), rel(o + i * 8 + 4),
+                           rel(o + i * 8 + 7), rel(o + i * 8 + 3), rel(o + i * 8 + 5));
+            }
+        }
+    }
+    return APX_OK;
+}
+
+}  // namespace apx

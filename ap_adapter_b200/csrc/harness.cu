@@ -92,14 +92,31 @@ static int compare(const char* what, const std::vector<float>& got, const std::v
     return ok ? 0 : 1;
 }
 
+// Stream every apx call of a case goes to (null = legacy default stream); time_ms switches it to a capturing stream.
+static cudaStream_t g_stream = nullptr;
+
+// Device time per call: `iters` calls are captured into ONE CUDA graph and the graph is replayed, so that host-side
+// submission cost (tensor-map encoding, launch) cannot bound the measurement of microsecond-scale kernels.
 static float time_ms(const std::function<int()>& fn, int iters = 20) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int i = 0; i < 3; ++i) if (fn()) return -1.f;
-    cudaEventRecord(a);
-    for (int i = 0; i < iters; ++i) if (fn()) return -1.f;
-    cudaEventRecord(b); cudaEventSynchronize(b);
+    for (int i = 0; i < 2; ++i) if (fn()) return -1.f;
+    cudaDeviceSynchronize();
+    cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    g_stream = st;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    for (int i = 0; ok && i < iters; ++i) ok = fn() == 0;
+    g_stream = nullptr;
+    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !ok || !graph) { printf("  graph capture failed: %s\n", cudaGetErrorString(cudaGetLastError())); return -1.f; }
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { printf("  graph instantiate failed\n"); return -1.f; }
+    cudaGraphLaunch(exec, st); cudaStreamSynchronize(st);
+    const int reps = 5;
+    cudaEventRecord(a, st);
+    for (int i = 0; i < reps; ++i) cudaGraphLaunch(exec, st);
+    cudaEventRecord(b, st); cudaEventSynchronize(b);
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
-    return ms / iters;
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(st);
+    return ms / (iters * reps);
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM
@@ -117,7 +134,7 @@ static int case_gemm(int M, int N, int K, int dt, int out_dt, bool bias, int epi
     CK(cudaMemset(o_tc, 0xFF, osz)); CK(cudaMemset(o_simt, 0xFF, osz));
     auto run = [&](int impl, void* out) -> int {
         AK(apx_set_impl(impl));
-        AK(apx_linear(dA, K, dW, K, bias ? db : nullptr, resid ? dres : nullptr, N, out, N, M, N, K, dt, out_dt, epi, nullptr));
+        AK(apx_linear(dA, K, dW, K, bias ? db : nullptr, resid ? dres : nullptr, N, out, N, M, N, K, dt, out_dt, epi, g_stream));
         return 0;
     };
     if (run(APX_IMPL_SIMT, o_simt)) return 1;
@@ -225,8 +242,8 @@ static int case_site(int Bc, int S, int C, int H, int Lt, int La, int dt, bool c
     // i = 0: product path (fused kernel when covered), 1: CUDA-core cross-check, 2: three tcgen05 kernels
     auto run = [&](int impl, int i, bool build_cache) -> int {
         AK(apx_set_impl(impl));
-        if (build_cache) AK(apx_ctx_kv(dctx, dWk, dWv, dWki, dWvi, cache[i], Bc, Lt, La, D, C, H, dt, ws, wsb, nullptr));
-        AK(apx_ipattn_fwd(dX, dWq, cache[i], dWo, impl == APX_IMPL_TC ? wpack : nullptr, dbo, Y[i], Bc, S, C, H, Lt, La, ap, dt, ws, wsb, nullptr));
+        if (build_cache) AK(apx_ctx_kv(dctx, dWk, dWv, dWki, dWvi, cache[i], Bc, Lt, La, D, C, H, dt, ws, wsb, g_stream));
+        AK(apx_ipattn_fwd(dX, dWq, cache[i], dWo, impl == APX_IMPL_TC ? wpack : nullptr, dbo, Y[i], Bc, S, C, H, Lt, La, ap, dt, ws, wsb, g_stream));
         return 0;
     };
     if (run(APX_IMPL_SIMT, 1, true)) return 1;

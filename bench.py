@@ -154,9 +154,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ our arm
 def site_roofline(batch: int, iters: int = 30) -> dict:
     """The dominant kernel of the hot path: the adapter site at the S=1000, C=256 geometry (10 of the 32 sites, and the
-    one that moves the most bytes).  Timed through apx_ipattn_fwd on the current stream with CUDA events, rotating over
-    enough distinct copies of every operand (X, Y, Wq, Wo, context cache, workspace) that no launch finds its inputs
-    in the 126 MB L2."""
+    one that moves the most bytes).  Timed through apx_ipattn_fwd with CUDA events around replays of a CUDA graph that
+    rotates over enough distinct copies of every operand (X, Y, Wq, Wo, context cache, workspace) that no launch finds
+    its inputs in the 126 MB L2."""
     from ap_adapter_b200 import _lib
 
     lib = _lib.load()
@@ -189,21 +189,29 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
     def launch(i):
         _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x[i]), _lib.ptr(wq[i]), _lib.ptr(cache[i]), _lib.ptr(wo[i]),
                                       _lib.ptr(pack[i]) if fused else None, _lib.ptr(bo), _lib.ptr(y[i]), bc, s, c, h, LT, LA,
-                                      AP_SCALE, 0, _lib.ptr(ws[i]), wsb, st), "apx_ipattn_fwd")
+                                      AP_SCALE, 0, _lib.ptr(ws[i]), wsb, _lib.stream_ptr()), "apx_ipattn_fwd")   # the CURRENT stream: capture
 
     for i in range(r):
         launch(i)
+    torch.cuda.synchronize()
+    # One CUDA graph holds r launches (one per operand copy); replaying it removes the host-side submission cost (ctypes call,
+    # tensor-map encoding), which would otherwise bound the measurement of a microsecond-scale kernel.
     n0 = _lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(r):
+            launch(i)
+    launches_per_call = (_lib.launch_count() - n0) // r
+    for _ in range(3):
+        graph.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    n = iters * r
-    for k in range(n):
-        launch(k % r)
+    for _ in range(iters):
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / n
-    launches_per_call = (_lib.launch_count() - n0) // n
+    us = 1e3 * e0.elapsed_time(e1) / (iters * r)
     l_tot = LT + LA
     flops = 4.0 * bc * s * c * c + 4.0 * bc * s * l_tot * c                # q-proj + out-proj + QK^T + PV
     l_pad = (LT + 15) // 16 * 16 + (LA + 15) // 16 * 16
@@ -216,7 +224,7 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
         achieved, peak, unit = flops / (us * 1e-6) / 1e12, pk["tflops"], "TFLOP/s"
     else:
         achieved, peak, unit = byts / (us * 1e-6) / 1e9, pk["hbm_gbs"], "GB/s"
-    name = "ipattn_fused_kernel (to_q + dual softmax(QK^T)V + ap_scale add + to_out in one tcgen05 kernel)" if fused else \
+    name = "ipattn_site_kernel (to_q + dual softmax(QK^T)V + ap_scale add + to_out in one tcgen05 kernel)" if fused else \
         "gemm_tc + ipattn_core + gemm_tc"
     return {"kernel": f"{name} via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
             "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),

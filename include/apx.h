@@ -11,7 +11,7 @@
  * Reference interfaces replaced (paths relative to the AP-adapter repository):
  *   apx_ipattn_fwd        APadapter/ap_adapter/attention_processor.py:347-470
  *                         (IPAttnProcessor2_0.__call__: to_q, two SDPAs, scale-add, to_out)
- *   apx_ipattn_pack       one-time re-layout of attn.to_q.weight / attn.to_out[0].weight (:387,:457) for the fused kernel
+ *   apx_ipattn_pack       one-time re-layout of attn.to_q.weight / attn.to_out[0].weight (:387,:457) for the site kernel
  *   apx_ctx_kv            attention_processor.py:400-415,435-439 (to_k/to_v on the text rows,
  *                         to_k_ip/to_v_ip on the audio rows; timestep-invariant, cached)
  *   apx_linear            the nn.Linear dispatches on the path (attention_processor.py:387,457;
@@ -51,7 +51,7 @@ extern "C" {
 #define APX_EPI_GELU      1   /* exact erf GELU, applied after the bias                      */
 
 /* ---- kernel families ---------------------------------------------------------------- */
-#define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; fused site kernel when packed weights are given) */
+#define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; single site kernel when packed weights are given) */
 #define APX_IMPL_SIMT         1   /* plain CUDA-core kernels: device-side cross-check for tests                     */
 #define APX_IMPL_TC_UNFUSED   2   /* tcgen05 path as three kernels (to_q GEMM, attention core, to_out GEMM)         */
 
@@ -105,9 +105,9 @@ int apx_ctx_kv(const void* ctx, const void* Wk, const void* Wv, const void* Wk_i
 size_t apx_ctx_kv_workspace_bytes(int Bc, int Lt, int La, int C);
 
 /*
- * Pre-packed to_q / to_out weights of one adapter site for the fused kernel (build once per weight version).
+ * Pre-packed to_q / to_out weights of one adapter site for the single-kernel path (build once per weight version).
  * Wq, Wo [C, C] `dtype` contiguous (attn.to_q.weight, attn.to_out[0].weight).  apx_ipattn_pack_bytes returns 0
- * when the fused kernel does not cover (C, H) (then pass wpack = NULL below).
+ * when the site kernel does not cover (C, H) (then pass wpack = NULL below).
  */
 size_t apx_ipattn_pack_bytes(int C, int H);
 int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, int dtype, void* stream);

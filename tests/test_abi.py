@@ -42,12 +42,14 @@ def test_no_compute_queries_work_without_gpu():
     assert lib.apx_ctx_kv_bytes(2, 8, 128, 250, 8) == 0  # C not divisible by H
     assert lib.apx_ipattn_workspace_bytes(2, 1000, 256) >= 2 * 2 * 1000 * 256 * 2
     assert lib.apx_audiomae_workspace_bytes(1) > 513 * 3072 * 2
-    # fused-kernel coverage and packed-weight size: [H][C/64][8][d_pad][8] + [nsplit][H][d_pad/8][CN][8] 16-bit elements
+    # site-kernel coverage and packed-weight size: Wq as [C/64][8][H*d_pad][8] + Wo as [H*d_pad/8][C][8] 16-bit elements
     assert lib.apx_ipattn_pack_bytes(256, 8) == 2 * 256 * 256 * 2
-    assert lib.apx_ipattn_pack_bytes(320, 8) == 2 * (8 * 48 * 320 + 2 * 8 * 48 * 160)   # d = 40 padded to 48
-    assert lib.apx_ipattn_pack_bytes(640, 8) == 0                                        # Y accumulator exceeds TMEM
-    assert lib.apx_ipattn_fused_ok(256, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(384, 8, 8, 128) == 1
-    assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(640, 8, 8, 8) == 0
+    assert lib.apx_ipattn_pack_bytes(128, 8) == 2 * 128 * 128 * 2
+    assert lib.apx_ipattn_pack_bytes(320, 8) == 0 and lib.apx_ipattn_pack_bytes(384, 8) == 0   # C > 256: three-kernel path
+    assert lib.apx_ipattn_pack_bytes(640, 8) == 0
+    assert lib.apx_ipattn_fused_ok(256, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(256, 8, 8, 8) == 1
+    assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(384, 8, 8, 128) == 0
+    assert lib.apx_ipattn_fused_ok(640, 8, 8, 8) == 0
 
 
 def test_null_pointers_are_rejected_not_dereferenced():
