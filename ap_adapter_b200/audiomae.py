@@ -243,8 +243,10 @@ class AudioMAEConditionCTPoolRand(nn.Module):
                 representation = representation.to(pdt)  # a model cast with .to(dtype) returns that dtype
             if self.use_reg:
                 representation = self.regularization(representation)
+            # AudioMAE.py:207-212 builds the ones on the host and copies them over; created on the device here (same values,
+            # no host->device copy, CUDA-graph capturable)
             return [representation,
-                    torch.ones((representation.size(0), representation.size(1))).to(representation.device).float()]
+                    torch.ones((representation.size(0), representation.size(1)), device=representation.device, dtype=torch.float32)]
 
 
 def extract_kaldi_fbank_feature(waveform, sampling_rate, log_mel_spec):

@@ -288,7 +288,7 @@ int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_
 }
 
 struct MaeWorkspace {
-    size_t x, xn, qkv, att, hid, xf, total;
+    size_t x, xn, qkv, att, hid, xf, tiles, total;
 };
 static MaeWorkspace mae_ws(int B) {
     const size_t rows = static_cast<size_t>(B) * 513;
@@ -300,6 +300,7 @@ static MaeWorkspace mae_ws(int B) {
     w.att = off; off += align_up(rows * 768 * 2, 256);
     w.hid = off; off += align_up(rows * 3072 * 2, 256);
     w.xf = off;  off += align_up(rows * 768 * 4, 256);
+    w.tiles = off; off += align_up(attention_tc_tiles_bytes(B, 12, 64, 513), 256);   // K / V^T operand tiles of one ViT block
     w.total = off;
     return w;
 }
@@ -323,8 +324,12 @@ static int audiomae_encode_into(const float* mel, const apx_vit_weights* w, floa
         // x += proj(attn(LN1(x)))
         APX_STEP(apx_layernorm(x, k.ln1_w, k.ln1_b, xn, rows, 768, eps, dt, stream));
         APX_STEP(apx_linear(xn, 768, k.qkv_w, 768, k.qkv_b, nullptr, 0, qkv, 2304, rows, 2304, 768, dt, dt, APX_EPI_NONE, stream));
-        APX_STEP(apx_attention(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304,
-                               att, 513LL * 768, 768, B, 513, 12, 64, 513, 513, 1.0f, 0.0f, dt, stream));
+        if (current_impl() == APX_IMPL_SIMT)   // CUDA-core cross-check (shared-memory K/V, warp-shuffle softmax)
+            APX_STEP(apx_attention(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304,
+                                   att, 513LL * 768, 768, B, 513, 12, 64, 513, 513, 1.0f, 0.0f, dt, stream));
+        else                                   // product path: tcgen05 attention core, N = 513 keys in 128-column chunks
+            APX_STEP(attention_tc(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304, att,
+                                  513LL * 768, 768, B, 513, 12, 64, 513, dt, base + ws.tiles, static_cast<cudaStream_t>(stream)));
         APX_STEP(apx_linear(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, stream));
         // x += fc2(GELU(fc1(LN2(x))))
         APX_STEP(apx_layernorm(x, k.ln2_w, k.ln2_b, xn, rows, 768, eps, dt, stream));

@@ -40,7 +40,9 @@ constexpr int CHUNK = 128;  // KV columns per S tile
 
 struct AttnArgs {
     const uint8_t* tiles;  // packed K / V^T tiles, [Bc][H]{K tile, V^T tile}
-    void* O;               // [Bc, S, C]
+    void* O;               // [Bc, S, H*d] view: element strides o_bs (batch), o_rs (row)
+    int64_t o_bs, o_rs;
+    int64_t q_bs, q_rs;    // element strides of the Q view (only used by the manual staging path)
     int Bc, S, C, H;
     int Lt, La, Lt_pad, La_pad, L_pad, d, d_pad;
     float ap_scale;
@@ -98,7 +100,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
     }
     if (a.q_manual) {
         const int srow_q = m0 + t;
-        const uint16_t* qrow = a.Q + (static_cast<int64_t>(b) * a.S + srow_q) * a.C + h * a.d;
+        const uint16_t* qrow = a.Q + static_cast<int64_t>(b) * a.q_bs + static_cast<int64_t>(srow_q) * a.q_rs + h * a.d;
         for (int k = 0; k < a.d_pad / 8; ++k) {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (srow_q < a.S && h * a.d + k * 8 + 8 <= a.C) v = *reinterpret_cast<const uint4*>(qrow + k * 8);
@@ -224,7 +226,7 @@ ipattn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AttnArgs a) {
     const int srow = m0 + t;
     const float w0 = inv_l[0];
     const float w1 = a.ap_scale * inv_l[1];
-    uint16_t* orow = reinterpret_cast<uint16_t*>(a.O) + (static_cast<int64_t>(b) * a.S + srow) * a.C + h * a.d;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(a.O) + static_cast<int64_t>(b) * a.o_bs + static_cast<int64_t>(srow) * a.o_rs + h * a.d;
     for (int c = 0; c < a.d_pad; c += 16) {
         uint32_t r0[16], r1[16];
         if (a.Lt > 0) tmem_ld16(tmem_O0 + lane_taddr + c, r0);
@@ -311,14 +313,19 @@ int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void
     return APX_OK;
 }
 
-int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int S, int C, int H, int Lt, int La,
-                   float ap_scale, int dtype, cudaStream_t st) {
+// Q / O are [Bc, S, H*d] VIEWS (element strides q_bs / q_rs, o_bs / o_rs; head h at column h*d); C = H*d.
+static int attention_core_launch(const void* Q, int64_t q_bs, int64_t q_rs, const void* cache_tiles, void* O, int64_t o_bs,
+                                 int64_t o_rs, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
+                                 cudaStream_t st) {
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_core: dtype %d", dtype);
     APX_REQUIRE(H > 0 && C % H == 0, APX_EINVAL, "ipattn_core: C=%d not divisible by H=%d", C, H);
     const KvPackGeom g = kv_pack_geom(Lt, La, C, H);
     APX_REQUIRE(g.d % 8 == 0 && g.d_pad <= 80, APX_EUNSUPPORTED, "ipattn_core: head dim %d (need d %% 8 == 0, d <= 80)",
                 g.d);
     APX_REQUIRE(Lt + La > 0, APX_EINVAL, "ipattn_core: empty context");
+    APX_REQUIRE(q_rs % 8 == 0 && q_bs % 8 == 0 && o_rs % 8 == 0 && o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(O) & 15) == 0,
+                APX_EINVAL, "ipattn_core: Q / O rows must be 16-byte aligned");
     const size_t smem = 128 + 128u * g.d_pad * 2 + g.k_tile_bytes + g.v_tile_bytes + 128 * CHUNK * 2 + 64;
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "ipattn_core: context of %d+%d tokens needs %zu B of shared memory",
                 Lt, La, smem);
@@ -327,7 +334,7 @@ int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int 
     {
         // Q viewed as [Bc][C/8][S][8]: the box {8, 128, d_pad/8, 1} lands as [d_pad/8][128][8] = core-matrix order.
         uint64_t dims[4] = {8, static_cast<uint64_t>(S), static_cast<uint64_t>(C / 8), static_cast<uint64_t>(Bc)};
-        uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, 16, static_cast<uint64_t>(S) * C * 2};
+        uint64_t strides[3] = {static_cast<uint64_t>(q_rs) * 2, 16, static_cast<uint64_t>(q_bs) * 2};
         uint32_t box[4] = {8, 128, static_cast<uint32_t>(g.d_pad / 8), 1};
         int rc = encode_tmap(&tmQ, dtype, 4, Q, dims, strides, box, 0);
         if (rc) return rc;
@@ -335,6 +342,7 @@ int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int 
     AttnArgs a;
     a.tiles = static_cast<const uint8_t*>(cache_tiles);
     a.O = O;
+    a.o_bs = o_bs; a.o_rs = o_rs; a.q_bs = q_bs; a.q_rs = q_rs;
     a.Bc = Bc; a.S = S; a.C = C; a.H = H;
     a.Lt = Lt; a.La = La; a.Lt_pad = g.Lt_pad; a.La_pad = g.La_pad; a.L_pad = g.L_pad; a.d = g.d; a.d_pad = g.d_pad;
     a.ap_scale = ap_scale;
@@ -359,6 +367,56 @@ int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int 
     else               ipattn_core_kernel<512><<<grid, 128, smem, st>>>(tmQ, a);
     APX_LAUNCH_CHECK("ipattn_core_kernel");
     return APX_OK;
+}
+
+int ipattn_core_tc(const void* Q, const void* cache_tiles, void* O, int Bc, int S, int C, int H, int Lt, int La,
+                   float ap_scale, int dtype, cudaStream_t st) {
+    return attention_core_launch(Q, static_cast<int64_t>(S) * C, C, cache_tiles, O, static_cast<int64_t>(S) * C, C, Bc, S, C, H,
+                                 Lt, La, ap_scale, dtype, st);
+}
+
+// ---- plain multi-head self-attention on the same kernel (the AudioMAE ViT blocks: timm Attention, N = 513, d = 64) ----------
+// K / V are [B, L, H*d] views; they are re-laid into K / V^T operand tiles (one "audio" segment of L keys) in `tiles`.
+namespace {
+__global__ void kv_pack_views_kernel(const uint16_t* __restrict__ K, int64_t k_bs, int64_t k_rs, const uint16_t* __restrict__ V,
+                                     int64_t v_bs, int64_t v_rs, uint16_t* __restrict__ tiles, KvPackGeom g, int B) {
+    // one block per (batch, head, 8-key group): stage the 8 x d slab of K and of V, write both tile orders coalesced
+    __shared__ uint16_t sk[8][96 + 2], sv[8][96 + 2];
+    const int lg = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int l0 = lg * 8;
+    for (int i = threadIdx.x; i < 8 * g.d_pad; i += blockDim.x) {
+        const int r = i / g.d_pad, c = i % g.d_pad;
+        const int l = l0 + r;
+        const bool ok = l < g.La && c < g.d;
+        sk[r][c] = ok ? K[b * k_bs + static_cast<int64_t>(l) * k_rs + h * g.d + c] : uint16_t(0);
+        sv[r][c] = ok ? V[b * v_bs + static_cast<int64_t>(l) * v_rs + h * g.d + c] : uint16_t(0);
+    }
+    __syncthreads();
+    uint16_t* kt = tiles + (static_cast<size_t>(b) * g.H + h) * (g.bytes_per_bh / 2);
+    uint16_t* vt = kt + g.k_tile_bytes / 2;
+    for (int i = threadIdx.x; i < 8 * g.d_pad; i += blockDim.x) {
+        // K tile [d_pad/8][L_pad][8]: (dim group dg, key l, e) ; this block owns keys l0..l0+7
+        const int dg = i / 64, rem = i % 64, r = rem / 8, e = rem % 8;
+        kt[(static_cast<size_t>(dg) * g.L_pad + l0 + r) * 8 + e] = sk[r][dg * 8 + e];
+        // V^T tile [L_pad/8][d_pad][8]: (key group lg, dim, e = key within the group)
+        const int dim = i / 8, ee = i % 8;
+        vt[(static_cast<size_t>(lg) * g.d_pad + dim) * 8 + ee] = sv[ee][dim];
+    }
+}
+}  // namespace
+
+size_t attention_tc_tiles_bytes(int B, int H, int d, int L) { return static_cast<size_t>(B) * H * kv_pack_geom(0, L, H * d, H).bytes_per_bh; }
+
+int attention_tc(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V, int64_t v_bs,
+                 int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int H, int d, int L, int dtype, void* tiles,
+                 cudaStream_t st) {
+    APX_REQUIRE(d % 8 == 0 && d <= 80, APX_EUNSUPPORTED, "attention_tc: head dim %d", d);
+    const KvPackGeom g = kv_pack_geom(0, L, H * d, H);
+    kv_pack_views_kernel<<<dim3(g.L_pad / 8, H, B), 128, 0, st>>>(static_cast<const uint16_t*>(K), k_bs, k_rs,
+                                                                  static_cast<const uint16_t*>(V), v_bs, v_rs,
+                                                                  static_cast<uint16_t*>(tiles), g, B);
+    APX_LAUNCH_CHECK("kv_pack_views_kernel");
+    return attention_core_launch(Q, q_bs, q_rs, tiles, O, o_bs, o_rs, B, S, H * d, H, 0, L, 1.0f, dtype, st);
 }
 
 }  // namespace apx

@@ -58,6 +58,11 @@ KvPackGeom kv_pack_geom(int Lt, int La, int C, int H);
 
 int ipattn_core_tc(const void* Q, const void* cache, void* O, int Bc, int S, int C, int H, int Lt, int La,
                    float ap_scale, int dtype, cudaStream_t st);
+// plain self-attention (one softmax over L keys) on the tcgen05 attention core; `tiles` = attention_tc_tiles_bytes(...) scratch
+size_t attention_tc_tiles_bytes(int B, int H, int d, int L);
+int attention_tc(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V, int64_t v_bs,
+                 int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int H, int d, int L, int dtype, void* tiles,
+                 cudaStream_t st);
 int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void* cache, int Bc, int Lt, int La,
             int C, int H, int dtype, cudaStream_t st);
 

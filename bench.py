@@ -232,6 +232,44 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
             "floor_us": round(1e6 * max(t_tensor, t_hbm), 3), "peak_source": pk["source"], "operand_copies_rotated": r}
 
 
+def audiomae_timing(iters: int = 20) -> dict:
+    """The other half of the hot path: AudioMAE ViT-B encode + pooling (apx_audiomae_fwd) for one 10 s clip and for a batch of 8,
+    random-init weights, fp16 GEMM operands, CUDA-event timed over CUDA-graph replays.  Runs once per generation (2 forwards
+    in the reference, pipeline_audioldm2.py:928-929), so it is reported beside the per-step metric, not inside it."""
+    from ap_adapter_b200 import _lib
+    from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    enc = AudioMAEConditionCTPoolRand(checkpoint_path=None).to(dev).half().eval()
+    out = {"kernels": "patch_embed + 12 x (layernorm, gemm_tc qkv, kv_pack_views + ipattn_core (tcgen05, N=513), gemm_tc proj+res, layernorm, gemm_tc fc1+GELU, gemm_tc fc2+res) + layernorm + pool",
+           "flops_per_clip": 97.0e9}
+    for b in (1, 8):
+        mel = torch.randn(b, 1024, 128, device=dev) * 0.45 - 0.45
+        with torch.no_grad():
+            for _ in range(2):
+                enc(mel, time_pool=2, freq_pool=2)
+            torch.cuda.synchronize()
+            n0 = _lib.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                emb = enc(mel, time_pool=2, freq_pool=2)[0]
+            launches = _lib.launch_count() - n0
+            graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        assert torch.isfinite(emb).all()
+        ms = e0.elapsed_time(e1) / iters
+        out[f"b{b}"] = {"ms": round(ms, 4), "clips_per_s": round(b / ms * 1e3, 1), "tflops": round(97.0e9 * b / (ms * 1e-3) / 1e12, 2),
+                        "launches": launches}
+    return out
+
+
 def run_ours(args) -> dict:
     import torch.distributed as dist
 
@@ -344,6 +382,7 @@ def run_ours(args) -> dict:
     }
     if rank == 0:
         out["roofline"] = site_roofline(b)
+        out["audiomae"] = audiomae_timing()
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(b, steps=3, warmup=1, budget_s=25.0)
     if world > 1:
