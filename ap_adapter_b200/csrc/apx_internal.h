@@ -69,7 +69,8 @@ int kv_pack(const void* Kt, const void* Vt, const void* Ka, const void* Va, void
 // ---- adapter site in one kernel (apx_ipattn_site.cu): all-head projections + two softmax warpgroups ---------------
 struct SiteGeom {
     int ok, C, H, d, d_pad, Nq, n_kb;
-    size_t wq_chunk_bytes, wo_kstep_bytes, wq_bytes, wo_bytes, total;
+    int cs_ok[3];                       // cluster sizes 1, 2, 4 the shape supports
+    size_t wq_off[3], wo_off[3], total; // weight-pack sections per cluster size
 };
 SiteGeom site_geom(int C, int H);
 bool ipattn_site_supported(int C, int H, int Lt, int La);

@@ -42,11 +42,18 @@ SiteGeom site_geom(int C, int H) {
     if (Nq > 256) return g;
     g.ok = 1; g.C = C; g.H = H; g.d = d; g.d_pad = d_pad; g.Nq = Nq;
     g.n_kb = C / 64;
-    g.wq_chunk_bytes = static_cast<size_t>(Nq) * 128;            // [8 k-groups][Nq rows][8] x 2 B
-    g.wo_kstep_bytes = static_cast<size_t>(C) * 32;              // [2 k-groups][C rows][8] x 2 B
-    g.wq_bytes = g.wq_chunk_bytes * g.n_kb;
-    g.wo_bytes = g.wo_kstep_bytes * (Nq / 16);
-    g.total = g.wq_bytes + g.wo_bytes;
+    // One pair of sections (Wq, Wo) per supported cluster size cs = 1, 2, 4: the rows of Wq (heads) / the columns of Wo are grouped
+    // by the CTA rank that owns them, so that every CTA streams only its own slice with 1-D bulk copies.
+    size_t off = 0;
+    for (int i = 0; i < 3; ++i) {
+        const int cs = 1 << i;
+        g.cs_ok[i] = (H % cs == 0) && ((C / cs) % 64 == 0) && ((Nq / cs) % 16 == 0);
+        g.wq_off[i] = g.wo_off[i] = 0;
+        if (!g.cs_ok[i]) continue;
+        g.wq_off[i] = off; off += static_cast<size_t>(Nq) * C * 2;   // [cs][C/64][8][Nq/cs][8]
+        g.wo_off[i] = off; off += static_cast<size_t>(Nq) * C * 2;   // [cs][Nq/8][C/cs][8]
+    }
+    g.total = off;
     return g;
 }
 
@@ -58,38 +65,46 @@ constexpr int NTHREADS = 384;          // 3 warpgroups: two softmax warpgroups +
 constexpr int REGS_WG = 216;           // setmaxnreg: the softmax warpgroups keep a 144-column score row in registers,
 constexpr int REGS_AUX = 72;           // the single-thread roles give their registers up (registers freed: (168-72)*128 = registers claimed: (216-168)*256)
 
-// WQ section: [C/64][8][Nq][8]: element (chunk kb, k-group kg, row n, e) = Wq[h*d + j, kb*64 + kg*8 + e], n = h*d_pad + j
-//             (rows with j >= d are zero).
-// WO section: [Nq/8][C][8]:     element (k-group kg, column n, e) = Wo[n, h*d + j], kg*8 + e = h*d_pad + j (zero for j >= d).
-__global__ void site_pack_kernel(const uint16_t* __restrict__ Wq, const uint16_t* __restrict__ Wo,
-                                 uint16_t* __restrict__ wq_out, uint16_t* __restrict__ wo_out, SiteGeom g) {
-    const size_t n_wq = g.wq_bytes / 2, n_wo = g.wo_bytes / 2;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_wq + n_wo;
+// Per cluster size cs (G = Nq / cs rows of Wq, cn = C / cs columns of Wo per CTA):
+// WQ section: [cs][C/64][8][G][8]: element (rank r, chunk kb, k-group kg, row n, e) = Wq[h*d + j, kb*64 + kg*8 + e] with
+//             r*G + n = h*d_pad + j (rows with j >= d are zero).
+// WO section: [cs][Nq/8][cn][8]:   element (rank r, k-group kg, column n, e) = Wo[r*cn + n, h*d + j], kg*8 + e = h*d_pad + j
+//             (zero for j >= d).
+__global__ void site_pack_kernel(const uint16_t* __restrict__ Wq, const uint16_t* __restrict__ Wo, uint16_t* __restrict__ out,
+                                 SiteGeom g) {
+    const size_t n_sec = static_cast<size_t>(g.Nq) * g.C;   // elements per section
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < 6 * n_sec;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        if (idx < n_wq) {
-            size_t r = idx;
-            const int e = r % 8; r /= 8;
-            const int n = r % g.Nq; r /= g.Nq;
-            const int kg = r % 8;
-            const int kb = r / 8;
-            const int h = n / g.d_pad, j = n % g.d_pad;
+        const int sec = static_cast<int>(idx / n_sec);   // 0: Wq cs=1, 1: Wo cs=1, 2: Wq cs=2, ...
+        const int i = sec >> 1, cs = 1 << i;
+        if (!g.cs_ok[i]) continue;
+        size_t r = idx % n_sec;
+        const int e = r % 8; r /= 8;
+        if ((sec & 1) == 0) {
+            const int G = g.Nq / cs;
+            const int n = r % G; r /= G;
+            const int kg = r % 8; r /= 8;
+            const int kb = r % (g.C / 64);
+            const int rank = r / (g.C / 64);
+            const int row = rank * G + n;
+            const int h = row / g.d_pad, j = row % g.d_pad;
             const int k = kb * 64 + kg * 8 + e;
-            wq_out[idx] = j < g.d ? Wq[static_cast<size_t>(h * g.d + j) * g.C + k] : uint16_t(0);
+            out[g.wq_off[i] / 2 + idx % n_sec] = j < g.d ? Wq[static_cast<size_t>(h * g.d + j) * g.C + k] : uint16_t(0);
         } else {
-            size_t r = idx - n_wq;
-            const int e = r % 8; r /= 8;
-            const int n = r % g.C;
-            const int kg = r / g.C;
+            const int cn = g.C / cs;
+            const int n = r % cn; r /= cn;
+            const int kg = r % (g.Nq / 8);
+            const int rank = r / (g.Nq / 8);
             const int kk = kg * 8 + e;
             const int h = kk / g.d_pad, j = kk % g.d_pad;
-            wo_out[idx - n_wq] = j < g.d ? Wo[static_cast<size_t>(n) * g.C + h * g.d + j] : uint16_t(0);
+            out[g.wo_off[i] / 2 + idx % n_sec] = j < g.d ? Wo[static_cast<size_t>(rank * cn + n) * g.C + h * g.d + j] : uint16_t(0);
         }
     }
 }
 
 struct SiteArgs {
-    const uint8_t* wq;     // packed WQ section
-    const uint8_t* wo;     // packed WO section
+    const uint8_t* wq;     // packed WQ section of this cluster size (rank-major)
+    const uint8_t* wo;     // packed WO section of this cluster size (rank-major)
     const uint8_t* tiles;  // packed context K / V^T tiles, [Bc][H]{K tile, V^T tile}
     const float* bo;       // fp32[C] or null
     int S, C, H, d_pad, dv_pad, Nq, n_kb;
@@ -97,6 +112,7 @@ struct SiteArgs {
     float ap_scale, scale_log2;
     uint32_t kv_bytes, k_tile_bytes, v_tile_bytes, vx_off, wq_chunk_bytes, wo_kstep_bytes, a_stage_bytes, p_bytes;
     int nk, nv, n_wo, wo_early;                // K ring, V ring depths; Wo stages / how many have their own region
+    int cs, hg, cn;                            // cluster size; heads and output columns per CTA (H / cs, C / cs)
     uint32_t off_p, off_k, off_v, off_bar;     // shared-memory offsets from the 1024-aligned base (sQO is at 0)
     uint32_t wo_off[4];                        // where each Wo stage lands
     long long* trace;                          // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0)
@@ -185,7 +201,7 @@ __device__ __forceinline__ void cvt_store16(const uint32_t* r, uint32_t dst) {  
 
 enum {  // mbarrier slots (40 x 8 bytes reserved; the TMEM slot and the bias slice follow)
     B_A_FULL = 0, B_K_FULL = 4, B_K_EMPTY = 7, B_V_FULL = 10, B_V_EMPTY = 13, B_WO_FULL = 16, B_Q = 20, B_SQ = 21, B_S_FULL = 22,
-    B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_COUNT = 33
+    B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_OALL = 33, B_DONE = 34, B_COUNT = 35
 };
 constexpr uint32_t BAR_REGION_BYTES = 384;   // barriers [0, 320) | TMEM slot at 320 | bias slice from 384
 
@@ -211,7 +227,10 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * 128;
+    // cluster of cs CTAs per tile: CTA `rank` owns heads [rank*hg, (rank+1)*hg) and output columns [rank*cn, (rank+1)*cn)
+    const int rank = a.cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int h_first = rank * a.hg;
+    const int m0 = (blockIdx.x / a.cs) * 128;
     const int b = blockIdx.y;
 
     if (threadIdx.x == 288) {
@@ -219,7 +238,8 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_prefetch_desc(&tmY);
 #pragma unroll 1
         for (int i = 0; i < B_COUNT; ++i) {
-            const uint32_t cnt = (i == B_SQ || i == B_SO_ALL) ? 256u : (i >= B_S_FREE && i < B_O_FULL) ? 128u : 1u;
+            const uint32_t cnt = (i == B_SQ || i == B_SO_ALL) ? 256u : (i >= B_S_FREE && i < B_O_FULL) ? 128u
+                                 : i == B_DONE ? static_cast<uint32_t>(a.cs > 1 ? a.cs - 1 : 1) : 1u;
             mbar_init(&bars[i], cnt);   // warpgroup -> MMA barriers count every arriving thread
         }
         fence_mbar_init();
@@ -231,6 +251,10 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Cluster handshake before the first remote write into a peer: every CTA's barriers must exist AND its phase-A stages (which
+    // overlay sQO) must be dead.  The warpgroup warps arrive once they have seen the Q accumulator complete, the other warps
+    // here; every warp waits (aligned) before this CTA pushes / before it leaves.
+    if (a.cs > 1 && warp >= 8) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     // phase A: Q at [0, Nq).  phase B: S(g) at g * L_pad, then {O_t(g), O_a(g)}, dv_pad columns each (column d_pad = row sum).
     // phase C: Y at [0, C).
@@ -248,16 +272,18 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 uint8_t* dst = smem + kb * a.a_stage_bytes;
                 mbar_expect_tx(&bars[B_A_FULL + kb], X_CHUNK_BYTES + a.wq_chunk_bytes);
                 tma_load_3d(dst, &tmX, kb * 64, m0, b, &bars[B_A_FULL + kb]);
-                tma_load_1d(dst + X_CHUNK_BYTES, a.wq + static_cast<size_t>(kb) * a.wq_chunk_bytes, a.wq_chunk_bytes,
+                tma_load_1d(dst + X_CHUNK_BYTES, a.wq + (static_cast<size_t>(rank) * a.n_kb + kb) * a.wq_chunk_bytes, a.wq_chunk_bytes,
                             &bars[B_A_FULL + kb]);
             }
-            mbar_wait_nocall(&bars[B_Q], 0);   // the Q accumulator is complete: the phase-A stages are dead
+            // the K / V rings and the early Wo stages may be filled at once when the phase-A stages end below them (cluster
+            // launches: small Wq slices); otherwise only when the Q accumulator is complete and the stages are dead
+            if (static_cast<uint32_t>(a.n_kb) * a.a_stage_bytes > a.off_k) mbar_wait_nocall(&bars[B_Q], 0);
             SITE_T(33);
-            const uint8_t* kv_src = a.tiles + static_cast<size_t>(b) * a.H * a.kv_bytes;
+            const uint8_t* kv_src = a.tiles + (static_cast<size_t>(b) * a.H + h_first) * a.kv_bytes;
             auto load_wo = [&](int w) {
                 const int ks = min(WO_KSTEPS_PER_STAGE, n_ko - w * WO_KSTEPS_PER_STAGE);
                 mbar_expect_tx(&bars[B_WO_FULL + w], ks * a.wo_kstep_bytes);
-                tma_load_1d(smem + a.wo_off[w], a.wo + static_cast<size_t>(w) * WO_KSTEPS_PER_STAGE * a.wo_kstep_bytes,
+                tma_load_1d(smem + a.wo_off[w], a.wo + (static_cast<size_t>(rank) * n_ko + w * WO_KSTEPS_PER_STAGE) * a.wo_kstep_bytes,
                             ks * a.wo_kstep_bytes, &bars[B_WO_FULL + w]);
             };
             // Issue order = the MMA thread's consumption order: K(2p), K(2p+1), then V(2p), V(2p+1) (a different order can
@@ -265,16 +291,16 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             int sk = 0, sv = 0;               // ring slots of the next K / V^T tile
             uint32_t pk = 1, pv = 1;          // "empty" parities of those slots (first pass: free)
 #pragma unroll 1
-            for (int h0 = 0; h0 < a.H; h0 += 2) {
+            for (int h0 = 0; h0 < a.hg; h0 += 2) {
 #pragma unroll 1
-                for (int h = h0; h < h0 + 2 && h < a.H; ++h) {
+                for (int h = h0; h < h0 + 2 && h < a.hg; ++h) {
                     mbar_wait_nocall(&bars[B_K_EMPTY + sk], pk);
                     mbar_expect_tx(&bars[B_K_FULL + sk], a.k_tile_bytes);
                     tma_load_1d(sK + sk * a.k_tile_bytes, kv_src + static_cast<size_t>(h) * a.kv_bytes, a.k_tile_bytes, &bars[B_K_FULL + sk]);
                     if (++sk == a.nk) { sk = 0; pk ^= 1; }
                 }
 #pragma unroll 1
-                for (int h = h0; h < h0 + 2 && h < a.H; ++h) {
+                for (int h = h0; h < h0 + 2 && h < a.hg; ++h) {
                     mbar_wait_nocall(&bars[B_V_EMPTY + sv], pv);
                     mbar_expect_tx(&bars[B_V_FULL + sv], a.v_tile_bytes);
                     tma_load_1d(sV + sv * a.v_tile_bytes, kv_src + static_cast<size_t>(h) * a.kv_bytes + a.vx_off, a.v_tile_bytes,
@@ -293,12 +319,12 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             for (int w = a.wo_early; w < a.n_wo; ++w) load_wo(w);
             SITE_T(36);
         }
+        if (a.cs > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     } else if (warp == 8) {
         // ================================================================ MMA issuer (one thread)
         if (elect_one()) {
-            const uint32_t idesc_q = umma_idesc_f16(FMT, 128, a.Nq);
+            const uint32_t idesc_q = umma_idesc_f16(FMT, 128, a.hg * a.d_pad);   // own heads only
             const uint32_t idesc_s = umma_idesc_f16(FMT, 128, a.L_pad);
-            const uint32_t idesc_y = umma_idesc_f16(FMT, 128, a.C);
             // ---- phase A: Q = X · Wq^T, all heads
             SITE_T(0);
 #pragma unroll 1
@@ -308,7 +334,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 if (kb == 0) SITE_T(1);
                 const uint32_t base = smem_u32(smem + kb * a.a_stage_bytes);
                 mma_chain(tmem_base, umma_desc(base, 16, 1024, kLayoutSW128),
-                          umma_desc(base + X_CHUNK_BYTES, a.Nq * 16, 128, kLayoutNone), 32, 2 * a.Nq * 16, 4, idesc_q,
+                          umma_desc(base + X_CHUNK_BYTES, a.hg * a.d_pad * 16, 128, kLayoutNone), 32, 2 * a.hg * a.d_pad * 16, 4, idesc_q,
                           static_cast<uint32_t>(kb));
             }
             umma_commit(&bars[B_Q]);
@@ -327,21 +353,21 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mbar_wait_nocall(&bars[B_SQ], 0);   // every Q column is in sQO; the Q accumulator columns are free
             tc_fence_after();
             SITE_T(3);
-            const int n_pairs = (a.H + 1) / 2;
+            const int n_pairs = (a.hg + 1) / 2;
 #pragma unroll 1
             for (int p = 0; p <= n_pairs; ++p) {
                 const uint32_t par = (p - 1) & 1;
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {   // scores of heads 2p, 2p+1
-                    const int h = 2 * p + g;
-                    if (h >= a.H) break;
+                    const int h = 2 * p + g;   // local head index; global head = h_first + h
+                    if (h >= a.hg) break;
                     if (p > 0) {   // S(h - 2) is in registers: its buffer is free
                         mbar_wait_nocall(&bars[B_S_FREE + g], par);
                         tc_fence_after();
                     }
                     mbar_wait_nocall(&bars[B_K_FULL + sk], pk);
                     tc_fence_after();
-                    mma_chain(tmem_base + g * a.L_pad, desc_add(dQO, h * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048,
+                    mma_chain(tmem_base + g * a.L_pad, desc_add(dQO, (h_first + h) * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048,
                               2 * a.L_pad * 16, a.d_pad / 16, idesc_s, 0);
                     umma_commit(&bars[B_S_FULL + g]);
                     umma_commit(&bars[B_K_EMPTY + sk]);
@@ -351,7 +377,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {   // P·V of heads 2p-2, 2p-1
                     const int h = 2 * (p - 1) + g;
-                    if (h >= a.H) break;
+                    if (h >= a.hg) break;
                     mbar_wait_nocall(&bars[B_P_FULL + g], par);   // P(h) is in shared memory, O(g) has been read
                     mbar_wait_nocall(&bars[B_V_FULL + sv], pv);
                     tc_fence_after();
@@ -370,9 +396,21 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             }
             umma_commit(&bars[B_PV_ALL]);
             // ---- phase C: Y = O · Wo^T
-            mbar_wait_nocall(&bars[B_SO_ALL], 0);   // every O_h is in sQO and every accumulator has been read
+            mbar_wait_nocall(&bars[B_SO_ALL], 0);   // every own O_h is in sQO and every accumulator has been read
             tc_fence_after();
             SITE_T(5);
+        }
+        if (a.cs > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // whole warp; see the handshake note above
+        if (elect_one()) {
+            const uint32_t idesc_y = umma_idesc_f16(FMT, 128, a.cn);             // own output columns only
+            const uint64_t dQO = umma_desc(smem_u32(sQO), 2048, 128, kLayoutNone);
+            const uint32_t head_bytes = (a.d_pad / 8) * 2048;
+            if (a.cs > 1) {
+                // the peers' O slices arrive by bulk copies over distributed shared memory (pushed head by head by their warpgroups)
+                mbar_expect_tx(&bars[B_OALL], static_cast<uint32_t>(a.cs - 1) * a.hg * head_bytes);
+                mbar_wait_nocall(&bars[B_OALL], 0);   // every peer's slices have landed here
+                tc_fence_after();
+            }
 #pragma unroll 1
             for (int i = 0; i < a.n_wo; ++i) {
                 const int ks = min(WO_KSTEPS_PER_STAGE, n_ko - i * WO_KSTEPS_PER_STAGE);
@@ -380,12 +418,23 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tc_fence_after();
                 if (i == 0) SITE_T(6);
                 mma_chain(tmem_base, desc_add(dQO, i * WO_KSTEPS_PER_STAGE * 2 * 2048),
-                          umma_desc(smem_u32(smem + a.wo_off[i]), a.C * 16, 128, kLayoutNone), 2 * 2048, a.wo_kstep_bytes, ks,
+                          umma_desc(smem_u32(smem + a.wo_off[i]), a.cn * 16, 128, kLayoutNone), 2 * 2048, a.wo_kstep_bytes, ks,
                           idesc_y, static_cast<uint32_t>(i));
             }
             umma_commit(&bars[B_Y]);
             SITE_T(7);
+            if (a.cs > 1) {
+                // tell every peer that its slices have landed here; leave only when every peer has said the same (then no bulk
+                // copy can still be reading this CTA's shared memory)
+                const uint32_t done = smem_u32(&bars[B_DONE]);
+#pragma unroll 1
+                for (int r = 0; r < a.cs; ++r)
+                    if (r != rank) mbar_arrive_remote(map_to_cta(done, r));
+                mbar_wait_nocall(&bars[B_DONE], 0);
+            }
         }
+    } else {   // warps 10, 11: idle
+        if (a.cs > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     } else {
         // ================================================================ the two softmax / conversion / epilogue warpgroups
@@ -403,11 +452,13 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
         // ---- phase A: Q accumulator -> 16-bit operand tile; the warpgroups split the 16-column groups
         {
-            const int n16 = a.Nq / 16, half = (n16 + 1) / 2;
+            const int n16 = a.hg * a.d_pad / 16, half = (n16 + 1) / 2;   // own heads' columns of the Q accumulator
             const int c_lo = g == 0 ? 0 : half, c_hi = g == 0 ? half : n16;
+            const uint32_t dst0 = sQO_row + (h_first * a.d_pad / 8) * 2048;   // own heads' slot of sQO
             if (t0) SITE_T(tb + 120);
             mbar_wait_nocall(&bars[B_Q], 0);
             tc_fence_after();
+            if (a.cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // phase-A stages are dead here
             if (t0) SITE_T(tb + 121);
 #pragma unroll 1
             for (int c0 = c_lo; c0 < c_hi; c0 += 8) {   // 8 loads per tcgen05.wait::ld: the round trip is the cost, not the bytes
@@ -418,7 +469,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (c0 + j < c_hi) { reg_tie16(r + j * 16); cvt_store16<FMT>(r + j * 16, sQO_row + (c0 + j) * 2 * 2048); }
+                    if (c0 + j < c_hi) { reg_tie16(r + j * 16); cvt_store16<FMT>(r + j * 16, dst0 + (c0 + j) * 2 * 2048); }
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -462,16 +513,30 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ra[j * 16 + i]), w_a, __uint_as_float(rt[j * 16 + i]) * w_t);
-                        store16<FMT>(sQO_row + (h * a.d_pad + c0 + j * 16) / 8 * 2048, v);
+                        store16<FMT>(sQO_row + ((h_first + h) * a.d_pad + c0 + j * 16) / 8 * 2048, v);
                     }
                 }
             }
+            if (a.cs > 1) {
+                // all-gather of the O slices over distributed shared memory, head by head: push this head's slice into every
+                // peer's sQO as soon as it exists; each copy completes its bytes on the peer's B_OALL barrier
+                fence_proxy_async_smem();
+                named_bar_sync(5 + g, 128);
+                if (t0) {
+                    const uint32_t head_bytes = (a.d_pad / 8) * 2048;
+                    const uint32_t slot = smem_u32(sQO) + (h_first + h) * head_bytes, bar = smem_u32(&bars[B_OALL]);
+#pragma unroll 1
+                    for (int r = 0; r < a.cs; ++r)
+                        if (r != rank) dsmem_bulk_copy(map_to_cta(slot, r), sQO + (h_first + h) * head_bytes, head_bytes, map_to_cta(bar, r));
+                }
+            }
         };
-        if (g == 1 && a.H > 1) named_bar_sync(2, 256);
+        if (g == 1 && a.hg > 2) named_bar_sync(2, 256);
+        bool cl_waited = false;
 #pragma unroll 1
         for (int it = 0;; ++it) {
-            const int h = g + 2 * it;
-            const bool live = h < a.H;
+            const int h = g + 2 * it;   // local head index
+            const bool live = h < a.hg;
             const int ts = tb + it * 8;
             const bool tr = t0 && it < 15 && live;
             float mx_t = -INFINITY, mx_a = -INFINITY;
@@ -513,12 +578,18 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 if (tr) SITE_T(ts + 2);
             }
             // the O of this warpgroup's previous head: its P·V ran under the code above; also frees this warpgroup's P tile
-            if (it > 0) convert_o(h - 2, (it - 1) & 1);
+            if (it > 0) {
+                if (a.cs > 1 && !cl_waited) {   // every peer's barriers exist and its phase-A stages are dead (see the handshake note)
+                    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                    cl_waited = true;
+                }
+                convert_o(h - 2, (it - 1) & 1);
+            }
             if (!live) break;
             if (tr) SITE_T(ts + 4);
             // One-time skew: warpgroup 1 starts when warpgroup 0 enters its first exponential pass, so that from then on one
             // warpgroup's MUFU-bound pass runs under the other's tensor-memory / conversion work instead of both in lockstep.
-            if (it == 0 && g == 0 && a.H > 1) named_bar_arrive(2, 256);
+            if (it == 0 && g == 0 && a.hg > 2) named_bar_arrive(2, 256);
             const float mxs_t = mx_t * sl, mxs_a = mx_a * sl;
             if (N16 > 0) {
 #pragma unroll
@@ -546,7 +617,8 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_before();
         mbar_arrive(&bars[B_SO_ALL]);
 
-        // ---- phase C epilogue: Y accumulator + bias -> 16 bit -> SWIZZLE_128B staging boxes (over sQO) -> TMA store
+        // ---- phase C epilogue: Y accumulator + bias -> 16 bit -> SWIZZLE_128B staging boxes -> TMA store
+        if (a.cs > 1 && !cl_waited) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         if (t0) SITE_T(tb + 123);
         mbar_wait_nocall(&bars[B_Y], 0);
         tc_fence_after();
@@ -554,10 +626,12 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         {
             // 64-column boxes alternate between the warpgroups; each box is converted by one warpgroup (4 loads, one round trip),
             // fenced, and stored by that warpgroup's first thread while the next box is being converted.
-            const uint32_t stage_row = smem_u32(sQO) + row * 128;
+            // staging boxes lie over the dead P / K / V / Wo regions (sQO may still be the source of this CTA's pushes)
+            const uint32_t stage_row = smem_u32(sP) + row * 128;
             const int sw = row & 7;
+            const int kb0 = rank * (a.cn / 64);   // first own 64-column box of Y
 #pragma unroll 1
-            for (int kb = g; kb < a.C / 64; kb += 2) {
+            for (int kb = g; kb < a.cn / 64; kb += 2) {
                 uint32_t r[64];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmem_ld16(tmem_base + lane_taddr + kb * 64 + j * 16, r + j * 16);
@@ -569,7 +643,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     uint32_t p[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float2 bb = *reinterpret_cast<const float2*>(sBias + kb * 64 + j * 16 + 2 * i);
+                        const float2 bb = *reinterpret_cast<const float2*>(sBias + (kb0 + kb) * 64 + j * 16 + 2 * i);
                         p[i] = pack2<FMT>(__uint_as_float(r[j * 16 + 2 * i]) + bb.x, __uint_as_float(r[j * 16 + 2 * i + 1]) + bb.y);
                     }
                     // 16-byte chunks 2j, 2j+1 of the 128-byte row; chunk k lives at k ^ (row & 7)  (SWIZZLE_128B)
@@ -579,7 +653,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 fence_proxy_async_smem();
                 named_bar_sync(3 + g, 128);
                 if (t0) {
-                    tma_store_3d(&tmY, sQO + kb * X_CHUNK_BYTES, kb * 64, m0, b);
+                    tma_store_3d(&tmY, sP + kb * X_CHUNK_BYTES, (kb0 + kb) * 64, m0, b);
                     tma_store_commit();
                 }
             }
@@ -602,25 +676,28 @@ struct SitePlan {
     uint32_t off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, smem_bytes, wo_off[4];
 };
 
-SitePlan site_plan(const SiteGeom& g, int Lt, int La) {
+SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs) {
     SitePlan p;
     memset(&p, 0, sizeof(p));
-    if (!g.ok || Lt < 0 || La < 0 || Lt + La <= 0) return p;
+    const int ci = cs == 1 ? 0 : cs == 2 ? 1 : cs == 4 ? 2 : -1;
+    if (!g.ok || ci < 0 || !g.cs_ok[ci] || Lt < 0 || La < 0 || Lt + La <= 0) return p;
     const KvPackGeom kg = kv_pack_geom(Lt, La, g.C, g.H);
     if (kg.L_pad < 16 || kg.L_pad > 256) return p;
     // tensor-memory columns of phase B: S(0) S(1) | O_t O_a (0) | O_t O_a (1)
     if (2 * kg.L_pad + 4 * kg.dv_pad > 512) return p;
     if (g.n_kb > 4) return p;
-    const uint32_t qo_bytes = static_cast<uint32_t>(std::max(g.Nq, g.C)) * 256;   // sQO, later the Y staging boxes
-    p.a_stage_bytes = X_CHUNK_BYTES + static_cast<uint32_t>(g.wq_chunk_bytes);
+    const uint32_t qo_bytes = static_cast<uint32_t>(std::max(g.Nq, g.C)) * 256;   // sQO: the full O tile of the query tile
+    p.a_stage_bytes = X_CHUNK_BYTES + static_cast<uint32_t>(g.Nq / cs) * 128;     // X chunk + own rows of the Wq chunk
     p.p_bytes = 128u * kg.L_pad * 2;
-    const uint32_t wo_stage = WO_KSTEPS_PER_STAGE * static_cast<uint32_t>(g.wo_kstep_bytes);
+    const uint32_t wo_stage = WO_KSTEPS_PER_STAGE * static_cast<uint32_t>(g.C / cs) * 32;
     p.n_wo = (g.Nq / 16 + WO_KSTEPS_PER_STAGE - 1) / WO_KSTEPS_PER_STAGE;
     if (p.n_wo > 4) return p;
     const uint32_t limit = 227u * 1024u - 1024u;   // minus the alignment slack of the dynamic shared-memory base
-    const int ring_max = std::min(3, g.H), ring_min = std::min(2, g.H);
-    for (int early = 1; early >= 0; --early)
+    const int ring_max = std::min(3, g.H / cs), ring_min = std::min(2, g.H / cs);
+    const int earlies[3] = {p.n_wo, 1, 0};         // Wo stages with a region of their own (prefetched right after phase A)
+    for (int ei = 0; ei < 3; ++ei)
         for (int ring = ring_max; ring >= ring_min; --ring) {
+            const int early = earlies[ei];
             uint32_t off = qo_bytes;
             p.off_p = off; off += static_cast<uint32_t>(align_up(2 * p.p_bytes, 1024));
             p.off_k = off; off += static_cast<uint32_t>(align_up(ring * kg.k_tile_bytes, 128));
@@ -628,8 +705,9 @@ SitePlan site_plan(const SiteGeom& g, int Lt, int La) {
             // Wo stages that are loaded after the last P·V lie over the dead P tiles and K / V rings (extended if those are small)
             off = std::max(off, p.off_p + (p.n_wo - early) * wo_stage);
             for (int i = early; i < p.n_wo; ++i) p.wo_off[i] = p.off_p + (i - early) * wo_stage;
-            if (early) { p.wo_off[0] = off; off += wo_stage; }   // a region of its own: prefetched right after phase A
+            for (int i = 0; i < early; ++i) { p.wo_off[i] = off; off += wo_stage; }
             off = std::max(off, static_cast<uint32_t>(g.n_kb) * p.a_stage_bytes);   // the phase-A stages overlay all of the above
+            off = std::max(off, p.off_p + static_cast<uint32_t>(g.C / cs / 64) * X_CHUNK_BYTES);   // and so do the Y staging boxes
             p.off_bar = static_cast<uint32_t>(align_up(off, 128));
             const uint32_t total = p.off_bar + BAR_REGION_BYTES + static_cast<uint32_t>(g.C) * 4;
             if (total <= limit) {
@@ -644,29 +722,42 @@ SitePlan site_plan(const SiteGeom& g, int Lt, int La) {
 
 bool ipattn_site_supported(int C, int H, int Lt, int La) {
     const SiteGeom g = site_geom(C, H);
-    return g.ok && site_plan(g, Lt, La).ok;
+    return g.ok && site_plan(g, Lt, La, 1).ok;
 }
 
 int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st) {
     const SiteGeom g = site_geom(C, H);
     APX_REQUIRE(g.ok, APX_EUNSUPPORTED, "ipattn_site_pack: the site kernel does not cover C=%d H=%d", C, H);
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site_pack: dtype %d", dtype);
-    const size_t total = g.total / 2;
-    const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8));
-    uint8_t* pb = static_cast<uint8_t*>(pack);
-    site_pack_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(Wq), static_cast<const uint16_t*>(Wo),
-                                             reinterpret_cast<uint16_t*>(pb), reinterpret_cast<uint16_t*>(pb + g.wq_bytes), g);
+    site_pack_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const uint16_t*>(Wq), static_cast<const uint16_t*>(Wo),
+                                              static_cast<uint16_t*>(pack), g);
     APX_LAUNCH_CHECK("site_pack_kernel");
     return APX_OK;
+}
+
+// Cluster size for a launch: the largest of {4, 2, 1} that divides the heads, leaves 64-column multiples per CTA and still fits
+// the grid into one wave of the 148 SMs (one CTA per SM); more CTAs per tile = a shorter per-CTA head loop.
+int ipattn_site_pick_cluster(int Bc, int S, int C, int H) {
+    static const int forced = [] { const char* e = getenv("APX_SITE_CLUSTER"); return e ? atoi(e) : 0; }();
+    const int tiles = ceil_div(S, 128) * Bc;
+    for (int cs = 4; cs >= 2; cs >>= 1) {
+        if (H % cs || (C / cs) % 64) continue;
+        if (forced == cs) return cs;
+        if (forced == 0 && tiles * cs <= 148) return cs;
+    }
+    return 1;
 }
 
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
                 int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st) {
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site: dtype %d", dtype);
+    int cs = ipattn_site_pick_cluster(Bc, S, C, H);
     const SiteGeom g = site_geom(C, H);
     APX_REQUIRE(g.ok, APX_EUNSUPPORTED, "ipattn_site: C=%d H=%d is not covered", C, H);
-    const SitePlan p = site_plan(g, Lt, La);
+    SitePlan p = site_plan(g, Lt, La, cs);
+    if (!p.ok && cs > 1) { cs = 1; p = site_plan(g, Lt, La, 1); }
     APX_REQUIRE(p.ok, APX_EUNSUPPORTED, "ipattn_site: context %d+%d does not fit the site kernel at C=%d", Lt, La, C);
+    const int ci = cs == 1 ? 0 : cs == 2 ? 1 : 2;
     APX_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(wpack) & 15) == 0 && (reinterpret_cast<uintptr_t>(cache_tiles) & 15) == 0,
                 APX_EINVAL, "ipattn_site: X / Y / pack / cache must be 16-byte aligned");
@@ -686,8 +777,8 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
     }
     SiteArgs a;
     const uint8_t* pb = static_cast<const uint8_t*>(wpack);
-    a.wq = pb;
-    a.wo = pb + g.wq_bytes;
+    a.wq = pb + g.wq_off[ci];
+    a.wo = pb + g.wo_off[ci];
     a.tiles = static_cast<const uint8_t*>(cache_tiles);
     a.bo = bo;
     a.S = S; a.C = C; a.H = H; a.d_pad = g.d_pad; a.dv_pad = kg.dv_pad; a.Nq = g.Nq; a.n_kb = g.n_kb;
@@ -698,11 +789,12 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
     a.k_tile_bytes = static_cast<uint32_t>(kg.k_tile_bytes);
     a.v_tile_bytes = static_cast<uint32_t>(kg.vx_tile_bytes);   // the site kernel streams the EXTENDED V^T tile
     a.vx_off = static_cast<uint32_t>(kg.k_tile_bytes + kg.v_tile_bytes);
-    a.wq_chunk_bytes = static_cast<uint32_t>(g.wq_chunk_bytes);
-    a.wo_kstep_bytes = static_cast<uint32_t>(g.wo_kstep_bytes);
+    a.wq_chunk_bytes = static_cast<uint32_t>(g.Nq / cs) * 128;    // [8 k-groups][Nq / cs rows][8] x 2 B
+    a.wo_kstep_bytes = static_cast<uint32_t>(C / cs) * 32;        // [2 k-groups][C / cs columns][8] x 2 B
     a.a_stage_bytes = p.a_stage_bytes;
     a.p_bytes = p.p_bytes;
     a.nk = p.nk; a.nv = p.nv; a.n_wo = p.n_wo; a.wo_early = p.wo_early;
+    a.cs = cs; a.hg = H / cs; a.cn = C / cs;
     a.off_p = p.off_p; a.off_k = p.off_k; a.off_v = p.off_v; a.off_bar = p.off_bar;
     for (int i = 0; i < 4; ++i) a.wo_off[i] = p.wo_off[i];
 
@@ -731,9 +823,21 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
                                               227 * 1024));
         attr_set = true;
     }
-    dim3 grid(ceil_div(S, 128), Bc);
     const KernelFn fn = table[(trace_on && dtype == APX_F16) ? 2 : (dtype == APX_F16 ? 0 : 1)][variant];
-    fn<<<grid, NTHREADS, p.smem_bytes, st>>>(tmX, tmY, a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(cs) * ceil_div(S, 128), Bc);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = p.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = static_cast<unsigned>(cs);
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmY, a));
     APX_LAUNCH_CHECK("ipattn_site_kernel");
     if (trace_on) {
         static int printed = 0;
@@ -743,8 +847,8 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
         if (printed++ < 2) {
             const long long t0 = t[0];
             auto rel = [&](int slot) { return t[slot] ? t[slot] - t0 : -1; };
-            printf("[apx site trace] Bc=%d S=%d C=%d H=%d Lt=%d La=%d ring=%d n_wo=%d (cycles since the MMA thread started; CTA 0)\n", Bc, S, C, H,
-                   Lt, La, p.nk, p.n_wo);
+            printf("[apx site trace] Bc=%d S=%d C=%d H=%d Lt=%d La=%d ring=%d n_wo=%d cluster=%d (cycles since the MMA thread started; CTA 0)\n", Bc, S, C, H,
+                   Lt, La, p.nk, p.n_wo, cs);
             printf("  mma : a_full0 %lld q_committed %lld sq_seen %lld (unused %lld) | so_all_seen %lld wo_full0 %lld y_committed %lld\n",
                    rel(1), rel(2), rel(3), rel(4), rel(5), rel(6), rel(7));
             for (int h = 0; h < H && h < 8; ++h) printf("  mma h%d: p_full_seen %lld issued %lld\n", h, rel(8 + 2 * h), rel(9 + 2 * h));

@@ -43,8 +43,9 @@ def test_no_compute_queries_work_without_gpu():
     assert lib.apx_ipattn_workspace_bytes(2, 1000, 256) >= 2 * 2 * 1000 * 256 * 2
     assert lib.apx_audiomae_workspace_bytes(1) > 513 * 3072 * 2
     # site-kernel coverage and packed-weight size: Wq as [C/64][8][H*d_pad][8] + Wo as [H*d_pad/8][C][8] 16-bit elements
-    assert lib.apx_ipattn_pack_bytes(256, 8) == 2 * 256 * 256 * 2
-    assert lib.apx_ipattn_pack_bytes(128, 8) == 2 * 128 * 128 * 2
+    # ... one (Wq, Wo) pair per supported cluster size (1, 2, 4 CTAs per query tile; C / cs must be a multiple of 64)
+    assert lib.apx_ipattn_pack_bytes(256, 8) == 3 * 2 * 256 * 256 * 2
+    assert lib.apx_ipattn_pack_bytes(128, 8) == 2 * 2 * 128 * 128 * 2
     assert lib.apx_ipattn_pack_bytes(320, 8) == 0 and lib.apx_ipattn_pack_bytes(384, 8) == 0   # C > 256: three-kernel path
     assert lib.apx_ipattn_pack_bytes(640, 8) == 0
     assert lib.apx_ipattn_fused_ok(256, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(256, 8, 8, 8) == 1

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(192, 1) ubench_kernel(Res* out) {
     tc_fence_after();
     const uint32_t tmem = *slot;
     uint32_t phase = 0;
-    if (warp == 1 && lane == 0) {
+    if (warp == 1 && elect_one()) {
         const int Ns[4] = {16, 32, 144, 256};
         const int ns[4] = {1, 2, 4, 16};
         for (int layout = 0; layout < 2; ++layout)
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) ubench_kernel(Res* out) {
         uint64_t* bar_never = bar + 3;   // never completes during the experiment; completed at the end to release the pollers
         if (threadIdx.x == 0) { mbar_init(bar_never, 1); fence_mbar_init(); }
         __syncthreads();
-        if (warp == 1 && lane == 0) {
+        if (warp == 1 && elect_one()) {
             const uint32_t idesc = umma_idesc_f16(0, 128, 32);
             const uint64_t da0 = umma_desc(smem_u32(sA), 2048, 128, kLayoutNone);
             const uint64_t db0 = umma_desc(smem_u32(sB), 32 * 16, 128, kLayoutNone);
