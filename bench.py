@@ -226,9 +226,16 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
         achieved, peak, unit = byts / (us * 1e-6) / 1e9, pk["hbm_gbs"], "GB/s"
     name = "ipattn_site_kernel (to_q + dual softmax(QK^T)V + ap_scale add + to_out in one tcgen05 kernel)" if fused else \
         "gemm_tc + ipattn_core + gemm_tc"
+    # DRAM traffic of the same launch from the committed ncu capture (null when this shape was not captured)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(f"ipattn_site_kernel Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} f16", {}).get("dram_bytes")
+    except (OSError, ValueError):
+        pass
     return {"kernel": f"{name} via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
             "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
-            "traffic": None, "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
+            "traffic": traffic, "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
             "floor_us": round(1e6 * max(t_tensor, t_hbm), 3), "peak_source": pk["source"], "operand_copies_rotated": r}
 
 
