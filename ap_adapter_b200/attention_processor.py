@@ -12,6 +12,8 @@ Differences that are deliberate (SURVEY.md §8 a-2'):
   (pipeline_audioldm2.py:1010-1017) and the reference's ``split`` hack (:424-428) is not reproduced.
 * the context K/V projections (attention_processor.py:406-407,435-436) are timestep-invariant; they are computed
   once per (context, weights) and cached on the processor instead of being recomputed every denoise step.
+* with gradients enabled (adapter training, train_apadapter_v2.py:892-979) the call goes through ``_IPAttnSiteFn``:
+  same forward kernels, ``apx_ipattn_bwd`` for dX / d to_k_ip.weight / d to_v_ip.weight; every other weight is frozen.
 """
 from __future__ import annotations
 
@@ -84,6 +86,52 @@ class AttnProcessor2_0(nn.Module):
         if attn.residual_connection:
             hidden_states = hidden_states + residual
         return hidden_states / attn.rescale_output_factor
+
+
+class _IPAttnSiteFn(torch.autograd.Function):
+    """One adapter site with gradients for adapter-only training (reference: train_apadapter_v2.py:892-979 backpropagates
+    through IPAttnProcessor2_0.__call__ with every UNet weight frozen).  Forward = the same libapx calls as inference
+    (context cache rebuilt from the current adapter weights, then apx_ipattn_fwd); backward = apx_ipattn_bwd, which returns
+    dX and the gradients of to_k_ip.weight / to_v_ip.weight."""
+
+    @staticmethod
+    def forward(ctx_, x, enc, wk_ip, wv_ip, proc, attn, heads, lt, la):
+        lib = _lib.load()
+        dtype = x.dtype
+        cache = proc._context_cache(attn, enc, heads, dtype)
+        wq, wo, wpack = proc._site_weights(attn, heads, dtype)
+        bo = attn.to_out[0].bias
+        bo = proc._bias_f32(bo) if bo is not None else None
+        bc, s, c = x.shape
+        y = torch.empty_like(x)
+        wsb = lib.apx_ipattn_workspace_bytes(bc, s, c)
+        work = _lib.workspace(wsb, x.device, "ipattn")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(wpack), _lib.ptr(bo),
+                                          _lib.ptr(y), bc, s, c, heads, lt, la, float(proc.scale), _lib.dtype_code(dtype),
+                                          _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_ipattn_fwd")
+        ctx_.save_for_backward(x, enc.detach().to(dtype).contiguous(), wq, wo, cache)
+        ctx_.meta = (heads, lt, la, float(proc.scale), wk_ip.dtype, wv_ip.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx_, dy):
+        lib = _lib.load()
+        x, enc, wq, wo, cache = ctx_.saved_tensors
+        heads, lt, la, scale, kdt, vdt = ctx_.meta
+        bc, s, c = x.shape
+        dctx = enc.shape[-1]
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x)
+        dwk = torch.empty((c, dctx), dtype=torch.float32, device=x.device)
+        dwv = torch.empty((c, dctx), dtype=torch.float32, device=x.device)
+        wsb = lib.apx_ipattn_bwd_workspace_bytes(bc, s, c, la)
+        work = _lib.workspace(wsb, x.device, "ipattn_bwd")
+        with torch.cuda.device(x.device):
+            _lib.check(lib.apx_ipattn_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(wq), _lib.ptr(wo), _lib.ptr(cache), _lib.ptr(enc),
+                                          _lib.ptr(dx), _lib.ptr(dwk), _lib.ptr(dwv), bc, s, c, heads, lt, la, dctx, scale,
+                                          _lib.dtype_code(x.dtype), _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_ipattn_bwd")
+        return dx, None, dwk.to(kdt), dwv.to(vdt), None, None, None, None, None
 
 
 class IPAttnProcessor2_0(nn.Module):
@@ -189,11 +237,8 @@ class IPAttnProcessor2_0(nn.Module):
                 "IPAttnProcessor2_0: attention_mask on the adapter site is not implemented (the AP-adapter pipeline never "
                 "passes one for the 768-d context; reference attention_processor.py:378-382,424-428 is a dead path)")
         _lib.require_cuda(hidden_states, encoder_hidden_states)
-        if torch.is_grad_enabled() and (hidden_states.requires_grad or self.to_k_ip.weight.requires_grad
-                                        or self.to_v_ip.weight.requires_grad):
-            raise NotImplementedError(
-                "IPAttnProcessor2_0: the sm_100a path is forward-only in this release; call it under torch.no_grad() "
-                "(adapter training backward is the next scope row, SURVEY.md §8f-1)")
+        needs_grad = torch.is_grad_enabled() and (hidden_states.requires_grad or self.to_k_ip.weight.requires_grad
+                                                  or self.to_v_ip.weight.requires_grad)
         residual = hidden_states
         if attn.spatial_norm is not None:
             hidden_states = attn.spatial_norm(hidden_states, temb)
@@ -212,6 +257,10 @@ class IPAttnProcessor2_0(nn.Module):
         if attn.norm_cross:
             encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
 
+        if hidden_states.dtype == torch.float32 and torch.is_autocast_enabled():
+            # training runs under bf16 / fp16 autocast with fp32 LayerNorm outputs (train_apadapter_v2.py:548-552): the linears
+            # of the reference processor would cast their inputs exactly like this
+            hidden_states = hidden_states.to(torch.get_autocast_gpu_dtype())
         dtype = hidden_states.dtype
         if dtype not in (torch.float16, torch.bfloat16):
             raise _lib.ApxError(f"IPAttnProcessor2_0: hidden_states dtype {dtype}; the kernels take float16 / bfloat16 "
@@ -228,9 +277,21 @@ class IPAttnProcessor2_0(nn.Module):
         la = encoder_hidden_states.shape[1] - lt
 
         lib = _lib.load()
-        cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
         if getattr(attn.to_q, "bias", None) is not None:
             raise _lib.ApxError(f"{self.name}: to_q with bias is not implemented (attention_bias=False in AudioLDM2)")
+        if needs_grad:
+            if la == 0:
+                raise _lib.ApxError(f"{self.name}: training needs audio tokens behind the {self.num_tokens} text tokens")
+            y = _IPAttnSiteFn.apply(x, encoder_hidden_states, self.to_k_ip.weight, self.to_v_ip.weight, self, attn, heads, lt, la)
+            hidden_states = attn.to_out[1](y)
+            if input_ndim == 4:
+                hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+            if attn.residual_connection:
+                hidden_states = hidden_states + residual
+            if attn.rescale_output_factor != 1.0:
+                hidden_states = hidden_states / attn.rescale_output_factor
+            return hidden_states
+        cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
         wq, wo, wpack = self._site_weights(attn, heads, dtype)
         bo = attn.to_out[0].bias
         if bo is not None:

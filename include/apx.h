@@ -11,6 +11,8 @@
  * Reference interfaces replaced (paths relative to the AP-adapter repository):
  *   apx_ipattn_fwd        APadapter/ap_adapter/attention_processor.py:347-470
  *                         (IPAttnProcessor2_0.__call__: to_q, two SDPAs, scale-add, to_out)
+ *   apx_ipattn_bwd        autograd of the same call in train_apadapter_v2.py:939-958 (accelerator.backward through the
+ *                         processor: dX, d to_k_ip.weight, d to_v_ip.weight)
  *   apx_ipattn_pack       one-time re-layout of attn.to_q.weight / attn.to_out[0].weight (:387,:457) for the site kernel
  *   apx_ctx_kv            attention_processor.py:400-415,435-439 (to_k/to_v on the text rows,
  *                         to_k_ip/to_v_ip on the audio rows; timestep-invariant, cached)
@@ -127,6 +129,18 @@ int apx_ipattn_fused_ok(int C, int H, int Lt, int La);
 size_t apx_ipattn_workspace_bytes(int Bc, int S, int C);
 int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
                    void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of one adapter site for adapter-only training (train_apadapter_v2.py:892-979: only to_k_ip / to_v_ip train, the
+ * UNet is frozen, and the loss must still reach the adapter sites further up, hence dX):
+ *   dY, X, dX [Bc, S, C] `dtype`; Wq, Wo [C, C] `dtype` (as in apx_ipattn_fwd); `cache` = the context cache the forward used
+ *   (apx_ctx_kv with the CURRENT adapter weights); ctx [Bc, Lt+La, Dctx] `dtype`; dWk_ip, dWv_ip fp32 [C, Dctx], overwritten.
+ * Requires La > 0, Lt + La <= 288, d % 8 == 0, C % 64 == 0.
+ */
+size_t apx_ipattn_bwd_workspace_bytes(int Bc, int S, int C, int La);
+int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo, const void* cache, const void* ctx, void* dX,
+                   float* dWk_ip, float* dWv_ip, int Bc, int S, int C, int H, int Lt, int La, int Dctx, float ap_scale, int dtype,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- AudioMAE encoder ---------------------------------------------------------------- */
