@@ -260,7 +260,7 @@ class IPAttnProcessor2_0(nn.Module):
         if hidden_states.dtype == torch.float32 and torch.is_autocast_enabled():
             # training runs under bf16 / fp16 autocast with fp32 LayerNorm outputs (train_apadapter_v2.py:548-552): the linears
             # of the reference processor would cast their inputs exactly like this
-            hidden_states = hidden_states.to(torch.get_autocast_gpu_dtype())
+            hidden_states = hidden_states.to(torch.get_autocast_dtype('cuda'))
         dtype = hidden_states.dtype
         if dtype not in (torch.float16, torch.bfloat16):
             raise _lib.ApxError(f"IPAttnProcessor2_0: hidden_states dtype {dtype}; the kernels take float16 / bfloat16 "

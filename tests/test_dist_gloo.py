@@ -70,3 +70,49 @@ def test_two_rank_sharded_denoise_equals_single_process(tmp_path):
     assert gathered.shape == single.shape == (N_CLIPS, 8, 24, 16)
     # per-clip arithmetic is independent of the batch it runs in (up to GEMM blocking on the CPU)
     assert ((gathered - single).abs().max() / single.abs().max()).item() < 1e-5
+
+
+# ---- adapter training, data parallel (BASELINE config 5): one flat all-reduce of the 64 adapter gradients per step -----------
+def _train_worker(rank, world, port, out_path):
+    from ap_adapter_b200 import training
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        unet, lat, gpe, pe, mask = _problem()          # identical initial weights on every rank (same seed)
+        unet.train(False)
+        params = training.freeze_all_but_adapter(unet)
+        assert len(params) == 64
+        w0 = [p.detach().clone() for p in params]
+        opt = torch.optim.SGD(params, lr=1e-1)
+        den = APAdapterDenoiser(unet)
+        lo, hi = shard_range(2, rank, world)            # one clip per rank
+        g = torch.Generator().manual_seed(100 + rank)   # different noise / timesteps per rank
+        # local gradients first (no collective), to know what the average must be
+        loss = training.train_step(unet, den.scheduler, torch.optim.SGD(params, lr=0.0), lat[lo:hi], gpe[lo:hi], pe[lo:hi],
+                                   mask[lo:hi], autocast_dtype=None, generator=g, params=params, max_grad_norm=None,
+                                   group=dist.new_group([rank]))
+        local = torch.cat([p.grad.reshape(-1) for p in params])
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, local)
+        want = sum(both) / world
+        # the real step: same noise (generator re-seeded), gradients averaged over the ranks, then SGD
+        g.manual_seed(100 + rank)
+        loss2 = training.train_step(unet, den.scheduler, opt, lat[lo:hi], gpe[lo:hi], pe[lo:hi], mask[lo:hi], autocast_dtype=None,
+                                    generator=g, params=params, max_grad_norm=None)
+        got = torch.cat([p.grad.reshape(-1) for p in params])
+        assert abs(loss - loss2) < 1e-6 * max(1.0, abs(loss))
+        assert ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item() < 1e-5
+        assert any((p.detach() - w).abs().max() > 0 for p, w in zip(params, w0))       # the step moved the adapter
+        torch.save(torch.cat([p.detach().reshape(-1) for p in params]), f"{out_path}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_adapter_training_averages_gradients(tmp_path):
+    out = str(tmp_path / "weights.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    w0, w1 = torch.load(out + ".0"), torch.load(out + ".1")
+    assert torch.equal(w0, w1)   # replicas stay bit-identical after the averaged step

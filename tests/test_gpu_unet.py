@@ -66,3 +66,34 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)
+
+
+def test_adapter_training_step_through_the_unet(setup):
+    """BASELINE config 5 on one GPU: one bf16-autocast optimiser step through the restated UNet with the sm_100a processors,
+    adapter-only gradients (train_apadapter_v2.py:892-979).  All 64 adapter tensors receive finite gradients, nothing else
+    does, and repeating the step on the same batch lowers the loss."""
+    from ap_adapter_b200 import training
+
+    unet, ours, _, inp = setup
+    unet.set_attn_processor(dict(ours))
+    unet.float()                                   # fp32 weights, bf16 autocast compute: the reference's mixed-precision setup
+    params = training.freeze_all_but_adapter(unet)
+    assert len(params) == 64 and sum(p.numel() for p in params) == 21_626_880
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-2)
+    den = APAdapterDenoiser(unet)
+    lat = inp["latents"].float()
+    gpe, pe = inp["gpe"][:1].float(), inp["pe"][:1].float()
+    mask = inp["mask"][:1]
+    gen = torch.Generator(device="cuda")
+    losses = []
+    n0 = _lib.launch_count()
+    for _ in range(3):
+        gen.manual_seed(7)                         # same noise and timesteps every step: the loss must go down
+        losses.append(training.train_step(unet, den.scheduler, opt, lat, gpe, pe, mask, generator=gen, params=params))
+    assert _lib.launch_count() > n0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+    assert all(p.grad is None for n, p in unet.named_parameters() if "processor" not in n)
+    assert losses[-1] < losses[0], losses
+    unet.half()
+    for p in unet.parameters():
+        p.requires_grad_(False)
