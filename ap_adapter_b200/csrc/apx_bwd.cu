@@ -27,7 +27,6 @@ __device__ __forceinline__ float warp_max_f(float v) {
 }
 
 constexpr int BWD_MAXJ = 9;    // keys per lane -> Lt + La <= 288
-constexpr int BWD_QPB = 32;    // query rows per block
 
 struct BwdArgs {
     const uint16_t* Q;    // [Bc, S, C]
@@ -40,20 +39,25 @@ struct BwdArgs {
     int S, C, H, d, L, Lt, La;
     float tau, ap_scale;
     int fmt, pitch;       // K / V row pitch in shared memory (16-bit elements)
-    int la_pitch;         // pitch of the [d][La] fp32 accumulators
 };
 
+// NJ = key groups of 32 a lane owns one key of (ceil(L / 32)), R = query rows per warp (4 warps per block).
+// Phase 1, per row: recompute scores and probabilities (two softmax segments), write dq, and KEEP for the lane's keys the two
+// coefficients the K / V gradients need (tau * ds_j and ap * p_j, zero for text keys) in registers.
+// Phase 2, per 8-dim chunk of the head: dK_a[j, c] += sum_rows coef_k[row][j] * q[row][c] (same for dV_a with dO) accumulates
+// in REGISTERS over the warp's rows, is reduced over the block's warps in shared memory and flushed with one global atomic
+// per (key, dim) per block.  (The first version did one shared-memory atomic per key, dim AND row: 2.3 ms per call.)
+template <int NJ, int R>
 __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     uint16_t* sK = reinterpret_cast<uint16_t*>(smem_bwd);
     uint16_t* sV = sK + static_cast<size_t>(a.L) * a.pitch;
-    float* sdK = reinterpret_cast<float*>(sV + static_cast<size_t>(a.L) * a.pitch);   // [d][la_pitch]: conflict-free per-key atomics
-    float* sdV = sdK + static_cast<size_t>(a.d) * a.la_pitch;
-    float* sq = sdV + static_cast<size_t>(a.d) * a.la_pitch;                           // [4 warps][2][d]: q and dO of the current row
+    float* sq = reinterpret_cast<float*>(sV + static_cast<size_t>(a.L) * a.pitch);   // [4 warps][R][2][d]: q and dO of the warp's rows
+    float* sred = sq + 4 * R * 2 * a.d;                                               // [2][NJ * 32][8]: block reduction of one chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
-    const int q0 = blockIdx.x * BWD_QPB;
+    const int q0 = blockIdx.x * (4 * R);
     const int dv = a.d / 8;
     const uint16_t* Kg = a.K + (static_cast<size_t>(b) * a.L) * a.C + h * a.d;
     const uint16_t* Vg = a.V + (static_cast<size_t>(b) * a.L) * a.C + h * a.d;
@@ -62,37 +66,52 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
         *reinterpret_cast<uint4*>(sK + l * a.pitch + c * 8) = *reinterpret_cast<const uint4*>(Kg + static_cast<size_t>(l) * a.C + c * 8);
         *reinterpret_cast<uint4*>(sV + l * a.pitch + c * 8) = *reinterpret_cast<const uint4*>(Vg + static_cast<size_t>(l) * a.C + c * 8);
     }
-    for (int i = threadIdx.x; i < 2 * a.d * a.la_pitch; i += 128) sdK[i] = 0.f;
     __syncthreads();
 
-    float* myq = sq + warp * 2 * a.d;
-    float* mydo = myq + a.d;
-    for (int qi = warp; qi < BWD_QPB; qi += 4) {
-        const int s = q0 + qi;
-        if (s >= a.S) break;   // warp-uniform
+    float ck[R][NJ], cv[R][NJ];   // tau * ds_j and ap * p_j of the lane's keys, per row (zero for text keys / missing rows)
+    float* wq = sq + warp * R * 2 * a.d;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int s = q0 + warp * R + r;
+        float* myq = wq + r * 2 * a.d;
+        float* mydo = myq + a.d;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) { ck[r][jj] = 0.f; cv[r][jj] = 0.f; }
+        if (s >= a.S) {   // warp-uniform; the row contributes nothing
+            for (int i = lane; i < 2 * a.d; i += 32) myq[i] = 0.f;
+            continue;
+        }
         const size_t rowoff = (static_cast<size_t>(b) * a.S + s) * a.C + h * a.d;
         for (int i = lane; i < a.d; i += 32) {
             myq[i] = ld16f(a.Q + rowoff, i, a.fmt);
             mydo[i] = ld16f(a.dO + rowoff, i, a.fmt);
         }
         __syncwarp();
-        // scores s_j = tau q.k_j and dp_j = w_seg * dO.v_j for the keys this lane owns (j = lane + 32 jj)
-        float sc[BWD_MAXJ], dp[BWD_MAXJ];
+        float sc[NJ], dp[NJ];
         float m_t = -INFINITY, m_a = -INFINITY;
 #pragma unroll
-        for (int jj = 0; jj < BWD_MAXJ; ++jj) {
+        for (int jj = 0; jj < NJ; ++jj) {
             const int j = jj * 32 + lane;
             float accs = -INFINITY, accd = 0.f;
             if (j < a.L) {
                 accs = 0.f;
                 const uint16_t* kr = sK + j * a.pitch;
                 const uint16_t* vr = sV + j * a.pitch;
-                for (int c = 0; c < a.d; c += 2) {
-                    float k0, k1, v0, v1;
-                    unpack16(*reinterpret_cast<const uint32_t*>(kr + c), a.fmt, k0, k1);
-                    unpack16(*reinterpret_cast<const uint32_t*>(vr + c), a.fmt, v0, v1);
-                    accs = fmaf(myq[c], k0, accs); accs = fmaf(myq[c + 1], k1, accs);
-                    accd = fmaf(mydo[c], v0, accd); accd = fmaf(mydo[c + 1], v1, accd);
+#pragma unroll 1
+                for (int c = 0; c < a.d; c += 8) {   // 128-bit K / V row reads (odd 16-byte pitch: conflict-free), q / dO broadcast
+                    const uint4 kv = *reinterpret_cast<const uint4*>(kr + c);
+                    const uint4 vv = *reinterpret_cast<const uint4*>(vr + c);
+                    const float4 qa = *reinterpret_cast<const float4*>(myq + c), qb = *reinterpret_cast<const float4*>(myq + c + 4);
+                    const float4 da = *reinterpret_cast<const float4*>(mydo + c), db = *reinterpret_cast<const float4*>(mydo + c + 4);
+                    float x0, x1;
+                    unpack16(kv.x, a.fmt, x0, x1); accs = fmaf(qa.x, x0, accs); accs = fmaf(qa.y, x1, accs);
+                    unpack16(kv.y, a.fmt, x0, x1); accs = fmaf(qa.z, x0, accs); accs = fmaf(qa.w, x1, accs);
+                    unpack16(kv.z, a.fmt, x0, x1); accs = fmaf(qb.x, x0, accs); accs = fmaf(qb.y, x1, accs);
+                    unpack16(kv.w, a.fmt, x0, x1); accs = fmaf(qb.z, x0, accs); accs = fmaf(qb.w, x1, accs);
+                    unpack16(vv.x, a.fmt, x0, x1); accd = fmaf(da.x, x0, accd); accd = fmaf(da.y, x1, accd);
+                    unpack16(vv.y, a.fmt, x0, x1); accd = fmaf(da.z, x0, accd); accd = fmaf(da.w, x1, accd);
+                    unpack16(vv.z, a.fmt, x0, x1); accd = fmaf(db.x, x0, accd); accd = fmaf(db.y, x1, accd);
+                    unpack16(vv.w, a.fmt, x0, x1); accd = fmaf(db.z, x0, accd); accd = fmaf(db.w, x1, accd);
                 }
                 accs *= a.tau;
                 if (j < a.Lt) m_t = fmaxf(m_t, accs); else { m_a = fmaxf(m_a, accs); accd *= a.ap_scale; }
@@ -103,7 +122,7 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
         m_a = warp_max_f(m_a);
         float l_t = 0.f, l_a = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < BWD_MAXJ; ++jj) {
+        for (int jj = 0; jj < NJ; ++jj) {
             const int j = jj * 32 + lane;
             float p = 0.f;
             if (j < a.L) {
@@ -117,7 +136,7 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
         const float il_t = a.Lt > 0 ? 1.f / l_t : 0.f, il_a = a.La > 0 ? 1.f / l_a : 0.f;
         float dl_t = 0.f, dl_a = 0.f;   // delta_seg = sum_j p_j dp_j
 #pragma unroll
-        for (int jj = 0; jj < BWD_MAXJ; ++jj) {
+        for (int jj = 0; jj < NJ; ++jj) {
             const int j = jj * 32 + lane;
             if (j < a.L) {
                 const float p = sc[jj] * (j < a.Lt ? il_t : il_a);
@@ -127,77 +146,104 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
         }
         dl_t = warp_sum_f(dl_t);
         dl_a = warp_sum_f(dl_a);
-        // ds_j = p_j (dp_j - delta); audio keys also feed dK_a += tau ds_j q and dV_a += ap p_j dO (this lane owns key j)
 #pragma unroll
-        for (int jj = 0; jj < BWD_MAXJ; ++jj) {
+        for (int jj = 0; jj < NJ; ++jj) {   // ds_j = p_j (dp_j - delta)
             const int j = jj * 32 + lane;
             float ds = 0.f;
             if (j < a.L) {
-                const float p = sc[jj];
-                ds = p * (dp[jj] - (j < a.Lt ? dl_t : dl_a));
-                if (j >= a.Lt) {
-                    const int ja = j - a.Lt;
-                    const float wk = a.tau * ds, wv = a.ap_scale * p;
-                    for (int c = 0; c < a.d; ++c) {
-                        atomicAdd(&sdK[c * a.la_pitch + ja], wk * myq[c]);
-                        atomicAdd(&sdV[c * a.la_pitch + ja], wv * mydo[c]);
-                    }
-                }
+                ds = sc[jj] * (dp[jj] - (j < a.Lt ? dl_t : dl_a));
+                if (j >= a.Lt) { ck[r][jj] = a.tau * ds; cv[r][jj] = a.ap_scale * sc[jj]; }
             }
             dp[jj] = ds;
         }
-        // dq = tau sum_j ds_j k_j : lanes over head dims, ds broadcast by shuffles
-        float dq[3] = {0.f, 0.f, 0.f};
+        // dq = tau sum_j ds_j k_j : the ds of the row go through shared memory, then lanes own PAIRS of head dims
+        float* sds = sq + 4 * R * 2 * a.d + 2 * NJ * 32 * 8 + warp * NJ * 32;
 #pragma unroll
-        for (int jj = 0; jj < BWD_MAXJ; ++jj) {
-            if (jj * 32 >= a.L) break;
-            const int lim = min(32, a.L - jj * 32);
-            for (int src = 0; src < lim; ++src) {
-                const float ds = __shfl_sync(0xffffffffu, dp[jj], src);
-                const uint16_t* kr = sK + (jj * 32 + src) * a.pitch;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int dim = lane + 32 * k;
-                    if (dim < a.d) dq[k] = fmaf(ds, ld16f(kr, dim, a.fmt), dq[k]);
-                }
-            }
-        }
+        for (int jj = 0; jj < NJ; ++jj) sds[jj * 32 + lane] = dp[jj];
+        __syncwarp();
         uint16_t* dqg = a.dQ + rowoff;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int dim = lane + 32 * k;
-            if (dim < a.d) {
-                const float v = dq[k] * a.tau;
-                if (a.fmt == 0) reinterpret_cast<__half*>(dqg)[dim] = __float2half_rn(v);
-                else reinterpret_cast<__nv_bfloat16*>(dqg)[dim] = __float2bfloat16_rn(v);
+        for (int dim = 2 * lane; dim < a.d; dim += 64) {
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < a.L; ++j) {
+                const float ds = sds[j];
+                float k0, k1;
+                unpack16(*reinterpret_cast<const uint32_t*>(sK + j * a.pitch + dim), a.fmt, k0, k1);
+                d0 = fmaf(ds, k0, d0);
+                d1 = fmaf(ds, k1, d1);
             }
+            *reinterpret_cast<uint32_t*>(dqg + dim) = pack16(d0 * a.tau, d1 * a.tau, a.fmt);
         }
         __syncwarp();
     }
-    __syncthreads();
-    // flush the block's dK_a / dV_a partial sums
-    for (int i = threadIdx.x; i < a.La * a.d; i += 128) {
-        const int ja = i / a.d, c = i % a.d;
-        const size_t g = (static_cast<size_t>(b) * a.La + ja) * a.C + h * a.d + c;
-        atomicAdd(&a.dKa[g], sdK[c * a.la_pitch + ja]);
-        atomicAdd(&a.dVa[g], sdV[c * a.la_pitch + ja]);
+    __syncwarp();
+
+    // ---- phase 2: dK_a / dV_a, one 8-dim chunk of the head at a time
+    for (int c0 = 0; c0 < a.d; c0 += 8) {
+        float ak[NJ][8], av[NJ][8];
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { ak[jj][c] = 0.f; av[jj][c] = 0.f; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 qa = *reinterpret_cast<const float4*>(wq + r * 2 * a.d + c0);
+            const float4 qb = *reinterpret_cast<const float4*>(wq + r * 2 * a.d + c0 + 4);
+            const float4 da = *reinterpret_cast<const float4*>(wq + r * 2 * a.d + a.d + c0);
+            const float4 db = *reinterpret_cast<const float4*>(wq + r * 2 * a.d + a.d + c0 + 4);
+            const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const float dov[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    ak[jj][c] = fmaf(ck[r][jj], qv[c], ak[jj][c]);
+                    av[jj][c] = fmaf(cv[r][jj], dov[c], av[jj][c]);
+                }
+        }
+        // reduce over the 4 warps in shared memory, then one global atomic per (key, dim)
+        __syncthreads();   // previous chunk's flush has finished reading sred
+        for (int i = threadIdx.x; i < 2 * NJ * 32 * 8; i += 128) sred[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                // [key][8]: the 8 dims of a key are contiguous; consecutive lanes = consecutive keys -> stride 8 words: 8-way
+                // bank conflict on plain stores, harmless for the few atomics left here
+                atomicAdd(&sred[(jj * 32 + lane) * 8 + c], ak[jj][c]);
+                atomicAdd(&sred[NJ * 32 * 8 + (jj * 32 + lane) * 8 + c], av[jj][c]);
+            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NJ * 32 * 8; i += 128) {
+            const int j = i / 8, c = i % 8;
+            if (j >= a.Lt && j < a.L && c0 + c < a.d) {
+                const size_t g = (static_cast<size_t>(b) * a.La + (j - a.Lt)) * a.C + h * a.d + c0 + c;
+                atomicAdd(&a.dKa[g], sred[i]);
+                atomicAdd(&a.dVa[g], sred[NJ * 32 * 8 + i]);
+            }
+        }
     }
 }
 
-// out[N1, N2] (fp32) = sum_m A[m, N1] (fp32) * B[row(m), N2] (16 bit), row(m) = (m / La) * L + Lt + m % La  (audio rows of ctx)
+// out[N1, N2] (fp32) += sum over this block's slice of m of A[m, N1] (fp32) * B[row(m), N2] (16 bit),
+// row(m) = (m / La) * L + Lt + m % La  (audio rows of ctx).  The token dimension is split over blockIdx.z (the output is
+// only C x 768: without the split 48 blocks would walk all tokens); `out` must be zeroed.
+constexpr int WGRAD_MSPLIT = 128;   // tokens per block
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A, const uint16_t* __restrict__ Bm, float* __restrict__ out,
                                                    int M, int N1, int N2, int La, int L, int Lt, int fmt) {
     __shared__ float sA[16][64 + 1];
     __shared__ float sB[16][64 + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int n1_0 = blockIdx.x * 64, n2_0 = blockIdx.y * 64;
+    const int m_lo = blockIdx.z * WGRAD_MSPLIT, m_hi = min(M, m_lo + WGRAD_MSPLIT);
     float acc[4][4] = {};
-    for (int m0 = 0; m0 < M; m0 += 16) {
+    for (int m0 = m_lo; m0 < m_hi; m0 += 16) {
         for (int i = threadIdx.x; i < 16 * 64; i += 256) {
             const int r = i >> 6, c = i & 63;
             const int m = m0 + r;
             float va = 0.f, vb = 0.f;
-            if (m < M) {
+            if (m < m_hi) {
                 if (n1_0 + c < N1) va = A[static_cast<size_t>(m) * N1 + n1_0 + c];
                 const size_t brow = static_cast<size_t>(m / La) * L + Lt + m % La;
                 if (n2_0 + c < N2) vb = ld16f(Bm, brow * N2 + n2_0 + c, fmt);
@@ -222,7 +268,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n1 = n1_0 + ty * 4 + i, n2 = n2_0 + tx * 4 + j;
-            if (n1 < N1 && n2 < N2) out[static_cast<size_t>(n1) * N2 + n2] = acc[i][j];
+            if (n1 < N1 && n2 < N2) atomicAdd(&out[static_cast<size_t>(n1) * N2 + n2], acc[i][j]);
         }
 }
 
@@ -312,19 +358,30 @@ int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo
     int p16 = d / 8 + 1;
     if (p16 % 2 == 0) ++p16;
     a.pitch = p16 * 8;
-    a.la_pitch = La + 1;
-    const size_t smem = static_cast<size_t>(L) * a.pitch * 2 * 2 + static_cast<size_t>(2) * d * a.la_pitch * 4 + 4 * 2 * d * 4;
+    const int nj = ceil_div(L, 32);
+    const int njt = nj <= 1 ? 1 : nj <= 2 ? 2 : nj <= 5 ? 5 : 9;   // instantiated key-group counts
+    const int rows = njt <= 5 ? 8 : 4;                             // query rows per warp (register budget of the coefficient cache)
+    const size_t smem = static_cast<size_t>(L) * a.pitch * 2 * 2 + static_cast<size_t>(4) * rows * 2 * d * 4 +
+                        static_cast<size_t>(2) * njt * 32 * 8 * 4 + static_cast<size_t>(4) * njt * 32 * 4;
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "apx_ipattn_bwd: context %d+%d at d=%d needs %zu B of shared memory", Lt, La, d, smem);
+    typedef void (*BwdFn)(BwdArgs);
+    const BwdFn fn = njt == 1 ? ipattn_bwd_kernel<1, 8> : njt == 2 ? ipattn_bwd_kernel<2, 8> : njt == 5 ? ipattn_bwd_kernel<5, 8>
+                                                                                                          : ipattn_bwd_kernel<9, 4>;
     static bool attr_set = false;
     if (!attr_set) {
-        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    ipattn_bwd_kernel<<<dim3(ceil_div(S, BWD_QPB), H, Bc), 128, smem, st>>>(a);
+    fn<<<dim3(ceil_div(S, 4 * rows), H, Bc), 128, smem, st>>>(a);
     APX_LAUNCH_CHECK("ipattn_bwd_kernel");
     rc = apx_linear(ws + w.dQ, C, ws + w.wqT, C, nullptr, nullptr, 0, dX, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
     if (rc) return rc;
-    dim3 wg(ceil_div(C, 64), ceil_div(Dctx, 64));
+    dim3 wg(ceil_div(C, 64), ceil_div(Dctx, 64), ceil_div(Bc * La, WGRAD_MSPLIT));
+    APX_CUDA(cudaMemsetAsync(dWk_ip, 0, static_cast<size_t>(C) * Dctx * 4, st));
+    APX_CUDA(cudaMemsetAsync(dWv_ip, 0, static_cast<size_t>(C) * Dctx * 4, st));
     wgrad_kernel<<<wg, 256, 0, st>>>(a.dKa, static_cast<const uint16_t*>(ctx), dWk_ip, Bc * La, C, Dctx, La, L, Lt, a.fmt);
     APX_LAUNCH_CHECK("wgrad_kernel");
     wgrad_kernel<<<wg, 256, 0, st>>>(a.dVa, static_cast<const uint16_t*>(ctx), dWv_ip, Bc * La, C, Dctx, La, L, Lt, a.fmt);
