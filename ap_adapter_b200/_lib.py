@@ -59,6 +59,7 @@ SYMBOLS = {
     "apx_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "apx_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _I, _P]),
     "apx_pool_tokens": (_I, [_P, _P, _I, _I, _I, _P]),
+    "apx_fbank": (_I, [_P, _I, _P, _P, _I, _P, _P]),
 }
 
 _lib = None

@@ -249,10 +249,36 @@ class AudioMAEConditionCTPoolRand(nn.Module):
                     torch.ones((representation.size(0), representation.size(1)), device=representation.device, dtype=torch.float32)]
 
 
+def kaldi_mel_banks(num_bins: int = 128, padded_window: int = 512, sample_freq: float = 16000.0, low_freq: float = 20.0,
+                    high_freq: float = 0.0) -> torch.Tensor:
+    """The mel filterbank of Kaldi's fbank as torchaudio builds it (``compliance/kaldi.py::get_mel_banks``, no VTLN):
+    triangular filters on the mel scale ``1127 ln(1 + f / 700)``; returns (num_bins, padded_window // 2 + 1) with a zero last
+    column (the Nyquist bin is dropped)."""
+    nyq = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyq
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)  # noqa: E731
+    lo, hi = float(mel(low_freq)), float(mel(high_freq))
+    delta = (hi - lo) / (num_bins + 1)
+    b = np.arange(num_bins, dtype=np.float64)[:, None]
+    left, center, right = lo + b * delta, lo + (b + 1.0) * delta, lo + (b + 2.0) * delta
+    n_fft = padded_window // 2
+    m = mel(sample_freq / padded_window * np.arange(n_fft, dtype=np.float64))[None, :]
+    up, down = (m - left) / (center - left), (right - m) / (right - center)
+    bins = np.maximum(0.0, np.minimum(up, down))
+    return torch.from_numpy(np.pad(bins, ((0, 0), (0, 1))).astype(np.float32))
+
+
+_MEL_FBT = {}
+
+
 def extract_kaldi_fbank_feature(waveform, sampling_rate, log_mel_spec):
     """Reference ``AudioMAE.py:356-394``: resample to 16 kHz, remove DC, Kaldi fbank (128 mel bins, hanning, 10 ms
-    shift), cut/pad to ``log_mel_spec.size(0)`` frames, normalise with the AudioSet statistics.  Runs wherever
-    ``waveform`` lives (torchaudio's Kaldi fbank is pure torch)."""
+    shift), cut/pad to ``log_mel_spec.size(0)`` frames, normalise with the AudioSet statistics.
+
+    A CUDA waveform runs through ``apx_fbank`` (one hand-written kernel: framing, DC removal, pre-emphasis, window, 512-point
+    DFT, mel filterbank, log, normalisation); a CPU waveform takes the reference's own route (torchaudio's Kaldi fbank on
+    the host, which is where ``pipeline_audioldm2.py:919-925`` computes it)."""
     import torchaudio
 
     norm_mean = -4.2677393
@@ -261,10 +287,22 @@ def extract_kaldi_fbank_feature(waveform, sampling_rate, log_mel_spec):
         waveform_16k = torchaudio.functional.resample(waveform, orig_freq=sampling_rate, new_freq=16000)
     else:
         waveform_16k = waveform
+    target_len = log_mel_spec.size(0)
+    if waveform_16k.is_cuda:
+        lib = _lib.load()
+        dev = waveform_16k.device
+        wav = waveform_16k.reshape(-1, waveform_16k.shape[-1])[0].float().contiguous()   # channel 0, as kaldi.fbank(channel=-1 -> 0)
+        if dev not in _MEL_FBT:
+            _MEL_FBT[dev] = kaldi_mel_banks().t().contiguous().to(dev)
+        out = torch.empty((target_len, 128), dtype=torch.float32, device=dev)
+        scratch = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.apx_fbank(_lib.ptr(wav), wav.numel(), _lib.ptr(_MEL_FBT[dev]), _lib.ptr(out), target_len, _lib.ptr(scratch),
+                                     _lib.stream_ptr()), "apx_fbank")
+        return out
     waveform_16k = waveform_16k - waveform_16k.mean()
     fbank = torchaudio.compliance.kaldi.fbank(waveform_16k, htk_compat=True, sample_frequency=16000, use_energy=False,
                                               window_type="hanning", num_mel_bins=128, dither=0.0, frame_shift=10)
-    target_len = log_mel_spec.size(0)
     p = target_len - fbank.shape[0]
     if p > 0:
         fbank = torch.nn.functional.pad(fbank, (0, 0, 0, p))

@@ -282,6 +282,10 @@ int apx_layernorm(const float* x, const float* w, const float* b, void* y, int r
                 "apx_layernorm: out_dtype %d", out_dtype);
     return layernorm(x, w, b, y, rows, cols, eps, out_dtype, static_cast<cudaStream_t>(stream));
 }
+int apx_fbank(const float* wave16k, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream) {
+    APX_REQUIRE(wave16k && mel_fbT && out && scratch, APX_EINVAL, "apx_fbank: null pointer");
+    return fbank(wave16k, n_samples, mel_fbT, out, target_len, scratch, static_cast<cudaStream_t>(stream));
+}
 int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_pool, void* stream) {
     APX_REQUIRE(xn && emb && B > 0, APX_EINVAL, "apx_pool_tokens: bad argument");
     return pool_tokens(xn, emb, B, time_pool, freq_pool, static_cast<cudaStream_t>(stream));

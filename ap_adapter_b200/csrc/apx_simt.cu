@@ -308,6 +308,82 @@ __global__ void __launch_bounds__(192) pool_tokens_kernel(const float* __restric
     reinterpret_cast<float4*>(emb + (static_cast<size_t>(b) * gridDim.x + tok) * 768)[c4] = o;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kaldi-compatible log-mel filterbank front-end (audio_encoder/AudioMAE.py:356-394 calls torchaudio.compliance.kaldi.fbank with
+// htk_compat, hanning window, 25 ms / 10 ms frames at 16 kHz, 128 mel bins, no dither): one block per output frame.
+//   frame = wave[i*160 : i*160+400] - global mean;  remove the frame's DC;  pre-emphasis 0.97 (first sample replicated);
+//   Hann window (non-periodic);  zero-pad to 512;  |DFT|^2 (direct summation with a shared twiddle table: 257 x 400 MACs);
+//   mel = fb[128 x 257] . power;  out = (log(max(mel, eps)) - norm_mean) / (2 norm_std);  frames past the signal are zero-padded
+//   BEFORE the normalisation, as the reference does.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wave_mean_kernel(const float* __restrict__ w, int n, float* __restrict__ mean) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) s += w[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        *mean = t / n;
+    }
+}
+
+__global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wave, int n_frames, const float* __restrict__ mean,
+                                                   const float* __restrict__ melT /* [257][128] */, float* __restrict__ out,
+                                                   float norm_mean, float norm_std2) {
+    __shared__ float x[512], y[512], ct[512], st[512], pw[257 + 3], red[8];
+    const int f = blockIdx.x, t = threadIdx.x;
+    float* orow = out + static_cast<size_t>(f) * 128;
+    if (f >= n_frames) {   // zero-padded frame
+        if (t < 128) orow[t] = (0.f - norm_mean) / norm_std2;
+        return;
+    }
+    const float gmean = *mean;
+    for (int i = t; i < 512; i += 256) {
+        x[i] = i < 400 ? wave[static_cast<size_t>(f) * 160 + i] - gmean : 0.f;
+        float sn, cs;
+        sincospif(static_cast<float>(i) / 256.0f, &sn, &cs);   // angle 2 pi i / 512
+        ct[i] = cs; st[i] = sn;
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = t; i < 400; i += 256) s += x[i];
+    s = warp_sum(s);
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    float fm = 0.f;
+    for (int i = 0; i < 8; ++i) fm += red[i];
+    fm *= (1.0f / 400.0f);
+    for (int i = t; i < 512; i += 256) {
+        float v = 0.f;
+        if (i < 400) {
+            const float cur = x[i] - fm, prev = x[i > 0 ? i - 1 : 0] - fm;
+            const float win = 0.5f - 0.5f * cospif(2.0f * i / 399.0f);   // torch.hann_window(400, periodic=False)
+            v = (cur - 0.97f * prev) * win;
+        }
+        y[i] = v;
+    }
+    __syncthreads();
+    for (int k = t; k <= 256; k += 256) {
+        float re = 0.f, im = 0.f;
+#pragma unroll 4
+        for (int n = 0; n < 400; ++n) {
+            const int idx = (k * n) & 511;
+            re = fmaf(y[n], ct[idx], re);
+            im = fmaf(y[n], st[idx], im);
+        }
+        pw[k] = re * re + im * im;
+    }
+    __syncthreads();
+    if (t < 128) {
+        float m = 0.f;
+        for (int k = 0; k < 257; ++k) m = fmaf(melT[k * 128 + t], pw[k], m);
+        orow[t] = (logf(fmaxf(m, 1.1920928955078125e-07f)) - norm_mean) / norm_std2;
+    }
+}
+
 }  // namespace
 
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
@@ -374,6 +450,17 @@ int pool_tokens(const float* xn, float* emb, int B, int tp, int fp, cudaStream_t
     const int ntok = (64 / tp) * (8 / fp);
     pool_tokens_kernel<<<dim3(ntok, B), 192, 0, st>>>(xn, emb, tp, fp);
     APX_LAUNCH_CHECK("pool_tokens_kernel");
+    return APX_OK;
+}
+
+int fbank(const float* wave16k, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st) {
+    APX_REQUIRE(n_samples >= 400, APX_EINVAL, "fbank: %d samples (one 25 ms frame needs 400)", n_samples);
+    APX_REQUIRE(target_len > 0, APX_EINVAL, "fbank: target_len=%d", target_len);
+    const int n_frames = 1 + (n_samples - 400) / 160;   // snip_edges
+    wave_mean_kernel<<<1, 256, 0, st>>>(wave16k, n_samples, scratch);
+    APX_LAUNCH_CHECK("wave_mean_kernel");
+    fbank_kernel<<<target_len, 256, 0, st>>>(wave16k, std::min(n_frames, target_len), scratch, melT, out, -4.2677393f, 2.0f * 4.5689974f);
+    APX_LAUNCH_CHECK("fbank_kernel");
     return APX_OK;
 }
 

@@ -22,6 +22,8 @@
  *                         (attention_processor.py:274,429,443; timm Attention in models_mae.py:566)
  *   apx_audiomae_fwd      audio_encoder/AudioMAE.py:190-212 (forward) -> :37-55 ->
  *                         audio_encoder/models_mae.py:548-570 (encoder) -> AudioMAE.py:148-182 (pool)
+ *   apx_fbank             audio_encoder/AudioMAE.py:356-394 (extract_kaldi_fbank_feature; torchaudio's Kaldi fbank is a
+ *                         third-party dependency of the reference, restated from torchaudio 2.x compliance/kaldi.py)
  *   apx_patch_embed       audio_encoder/models_mae.py:19-44 (PatchEmbed_org) + :552,561-563
  *   apx_layernorm         nn.LayerNorm(eps=1e-6) inside timm Block / models_mae.py:568
  *   apx_pool_tokens       audio_encoder/AudioMAE.py:148-182 (drop CLS, (avg+max)/2 pooling)
@@ -175,6 +177,15 @@ int apx_audiomae_fwd(const float* mel, const apx_vit_weights* w_host, float* emb
  * (audio_encoder/models_mae.py:548-570, forward_encoder_no_random_mask_no_average)                      */
 int apx_audiomae_encode(const float* mel, const apx_vit_weights* w_host, float* tokens, int B,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Kaldi-compatible log-mel front-end of the audio prompt (audio_encoder/AudioMAE.py:356-394 after the resampling:
+ * torchaudio.compliance.kaldi.fbank(htk_compat, hanning, 128 bins, 25 ms / 10 ms, no dither) -> cut / zero-pad to
+ * target_len frames -> (x + 4.2677393) / (2 * 4.5689974)).
+ *   wave16k fp32[n_samples] at 16 kHz (the global DC offset is removed inside); mel_fbT fp32[257, 128] = the mel filterbank
+ *   transposed (host-built, ap_adapter_b200/audiomae.py::kaldi_mel_banks); out fp32[target_len, 128]; scratch >= 4 bytes.
+ */
+int apx_fbank(const float* wave16k, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream);
 
 /* individual stages (also used by the parity tests) */
 int apx_patch_embed(const float* mel, const float* patch_wT, const float* patch_b,

@@ -112,3 +112,28 @@ def test_bad_arguments_raise(model):
     cpu_model = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=cases.mae_state_dict(depth=1), depth=1)
     with pytest.raises(_lib.ApxError, match="CPU"):
         cpu_model(cases.make_mel(), time_pool=2, freq_pool=2)
+
+
+# ---- audio front-end: Kaldi fbank on the GPU vs torchaudio on the host -----------------------------------------
+def _synthetic_wave(sr, seconds, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(int(sr * seconds)) / sr
+    w = 0.3 * torch.sin(2 * torch.pi * 440.0 * t) + 0.2 * torch.sin(2 * torch.pi * 3100.0 * t * (1 + 0.1 * t))
+    w = w + 0.05 * torch.randn(t.shape, generator=g) + 0.01          # broadband floor + a DC offset
+    return w.unsqueeze(0).float()
+
+
+@pytest.mark.parametrize("sr,seconds", [(16000, 10.0), (16000, 3.7), (44100, 10.0), (16000, 11.5)],
+                         ids=["16k_10s", "16k_short_padded", "44k1_resampled", "16k_long_cut"])
+def test_fbank_front_end_matches_torchaudio(sr, seconds):
+    """apx_fbank (CUDA) against the reference's own route: torchaudio's Kaldi fbank on the host (AudioMAE.py:356-394), incl.
+    zero-padding / cutting to 1024 frames and the AudioSet normalisation.  Tolerance 2e-3 absolute on the normalised log-mel
+    (values are O(1); the direct 512-point DFT and the fp32 mel sums differ from the host FFT in the last bits)."""
+    from ap_adapter_b200.audiomae import extract_kaldi_fbank_feature
+
+    wav = _synthetic_wave(sr, seconds, seed=sr + int(seconds))
+    ref = extract_kaldi_fbank_feature(wav, sr, torch.zeros(1024, 128))                  # CPU: torchaudio
+    n0 = _lib.launch_count()
+    got = extract_kaldi_fbank_feature(wav.cuda(), sr, torch.zeros(1024, 128))           # CUDA: libapx
+    assert _lib.launch_count() - n0 == 2 and got.is_cuda and got.shape == (1024, 128)
+    assert (got.cpu() - ref).abs().max().item() < 2e-3

@@ -183,3 +183,16 @@ def test_denoiser_conditioning_block_layout(tiny_unet):
     assert (out[:3, 8:] == 0).all() and (out[3:, 8:] == 2.0).all()
     lat = den.prepare_latents(3, 1000, torch.float32, "cpu", torch.Generator().manual_seed(0))
     assert lat.shape == (3, 8, 250, 16)
+
+
+def test_kaldi_mel_banks_match_torchaudio():
+    """The host-built mel filterbank that apx_fbank consumes restates torchaudio's ``get_mel_banks`` (the third-party routine
+    behind the reference's extract_kaldi_fbank_feature, AudioMAE.py:368-377)."""
+    from torchaudio.compliance import kaldi
+
+    from ap_adapter_b200.audiomae import kaldi_mel_banks
+
+    ref, _ = kaldi.get_mel_banks(128, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    ours = kaldi_mel_banks()
+    assert ours.shape == (128, 257) and torch.all(ours[:, 256] == 0)
+    assert (ours[:, :256] - ref).abs().max().item() < 5e-5
