@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libapx.so")
 
 APX_F16, APX_BF16, APX_F32 = 0, 1, 2
-APX_EPI_NONE, APX_EPI_GELU = 0, 1
+APX_EPI_NONE, APX_EPI_GELU, APX_EPI_GEGLU, APX_EPI_RES16 = 0, 1, 2, 4
 APX_IMPL_TC, APX_IMPL_SIMT, APX_IMPL_TC_UNFUSED = 0, 1, 2
 
 # every symbol include/apx.h declares: (restype, argtypes)
@@ -142,27 +142,35 @@ def launch_count() -> int:
 
 # ---- thin functional wrappers (used by the processors, the encoder and the tests) ----------------------
 def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
-           out_dtype: torch.dtype | None = None, gelu: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (apx_linear)."""
+           out_dtype: torch.dtype | None = None, gelu: bool = False, out: torch.Tensor | None = None,
+           geglu: bool = False) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (apx_linear).
+
+    geglu=True: rows of `w` are interleaved (hidden_0, gate_0, hidden_1, gate_1, ...) and the result has N/2 columns,
+    hidden * gelu(gate).  `residual` is fp32, or the output dtype (16-bit) — the flag APX_EPI_RES16 is derived from it."""
     lib = load()
     dev = require_cuda(a, w, bias, residual, out)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.dtype == w.dtype
+    assert not (gelu and geglu)
     a = a if a.stride(1) == 1 else a.contiguous()
     w = w if w.stride(1) == 1 else w.contiguous()
     m, k = a.shape
     n = w.shape[0]
     out_dtype = out_dtype or a.dtype
     if out is None:
-        out = torch.empty((m, n), dtype=out_dtype, device=dev)
+        out = torch.empty((m, n // 2 if geglu else n), dtype=out_dtype, device=dev)
+    epi = APX_EPI_GEGLU if geglu else APX_EPI_GELU if gelu else APX_EPI_NONE
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     if residual is not None:
-        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+        assert residual.stride(1) == 1 and residual.shape == out.shape
+        if residual.dtype != torch.float32:
+            assert residual.dtype == out.dtype and out.dtype != torch.float32
+            epi |= APX_EPI_RES16
     with torch.cuda.device(dev):
         check(lib.apx_linear(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(residual),
                              residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
-                             dtype_code(a.dtype), dtype_code(out.dtype), APX_EPI_GELU if gelu else APX_EPI_NONE,
-                             stream_ptr()), "apx_linear")
+                             dtype_code(a.dtype), dtype_code(out.dtype), epi, stream_ptr()), "apx_linear")
     return out
 
 

@@ -42,10 +42,33 @@ class AttnProcessor2_0(nn.Module):
     and stay a thin PyTorch module: cuBLAS projections + torch SDPA, with the reference's mask handling.
     """
 
+    # inference on CUDA: to_q/to_k/to_v of a self-attention site (to_k/to_v of a cross-attention site) run as ONE projection over
+    # the concatenated weight (what diffusers' fuse_qkv_projections() does); APX_QKV_FUSED=0 keeps the three separate GEMMs
+    fuse_projections = os.environ.get("APX_QKV_FUSED", "1") != "0"
+
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
         if not hasattr(F, "scaled_dot_product_attention"):
             raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
+        self._cat = None
+
+    def _cat_weight(self, mods):
+        key = tuple((m.weight._version, m.weight.data_ptr(), m.weight.dtype) for m in mods)
+        if self._cat is None or self._cat[0] != key:
+            self._cat = (key, torch.cat([m.weight.detach() for m in mods], dim=0).contiguous())
+        return self._cat[1]
+
+    def _project(self, attn, hidden_states, encoder_hidden_states, self_attention):
+        """(query, key, value) as (B, L, C) tensors (possibly strided views of one fused projection)."""
+        fused = (self.fuse_projections and hidden_states.is_cuda and not torch.is_grad_enabled()
+                 and attn.to_q.bias is None and attn.to_k.bias is None and attn.to_v.bias is None)
+        if fused and self_attention:
+            return F.linear(hidden_states, self._cat_weight((attn.to_q, attn.to_k, attn.to_v))).chunk(3, dim=-1)
+        query = attn.to_q(hidden_states)
+        if fused and encoder_hidden_states.dtype == attn.to_k.weight.dtype:
+            key, value = F.linear(encoder_hidden_states, self._cat_weight((attn.to_k, attn.to_v))).chunk(2, dim=-1)
+            return query, key, value
+        return query, attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         residual = hidden_states
@@ -65,13 +88,12 @@ class AttnProcessor2_0(nn.Module):
         if attn.group_norm is not None:
             hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
 
-        query = attn.to_q(hidden_states)
-        if encoder_hidden_states is None:
+        self_attention = encoder_hidden_states is None
+        if self_attention:
             encoder_hidden_states = hidden_states
         elif attn.norm_cross:
             encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
-        key = attn.to_k(encoder_hidden_states)
-        value = attn.to_v(encoder_hidden_states)
+        query, key, value = self._project(attn, hidden_states, encoder_hidden_states, self_attention)
         head_dim = key.shape[-1] // attn.heads
         query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
         key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)

@@ -128,7 +128,8 @@ int apx_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const flo
     APX_REQUIRE(A && W && out, APX_EINVAL, "apx_linear: null pointer");
     APX_REQUIRE(out_dtype == APX_F16 || out_dtype == APX_BF16 || out_dtype == APX_F32, APX_EINVAL,
                 "apx_linear: out_dtype %d", out_dtype);
-    APX_REQUIRE(epilogue == APX_EPI_NONE || epilogue == APX_EPI_GELU, APX_EINVAL, "apx_linear: epilogue %d", epilogue);
+    APX_REQUIRE((epilogue & ~7) == 0 && (epilogue & 3) != 3, APX_EINVAL, "apx_linear: epilogue %d", epilogue);
+    APX_REQUIRE((epilogue & 3) != APX_EPI_GEGLU || N % 32 == 0, APX_EUNSUPPORTED, "apx_linear: GEGLU needs N %% 32 == 0 (N=%d)", N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (current_impl() == APX_IMPL_SIMT)
         return gemm_simt(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue, st);

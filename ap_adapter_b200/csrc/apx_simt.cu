@@ -33,7 +33,7 @@ __device__ __forceinline__ float warp_max(float v) {
 struct SimtGemmArgs {
     const void* A; int64_t lda;
     const void* W; int64_t ldw;
-    const float* bias; const float* residual; int64_t ldr;
+    const float* bias; const void* residual; int64_t ldr;
     void* out; int64_t ldo;
     int M, N, K, in_fmt, out_dtype, epilogue;
 };
@@ -64,22 +64,39 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g) {
         }
         __syncthreads();
     }
+    const int epi = g.epilogue & 3;
+    auto put = [&](int m, int n, float v) {   // n = OUTPUT column
+        if (g.residual) {
+            const int64_t ro = static_cast<int64_t>(m) * g.ldr + n;
+            v += (g.epilogue & APX_EPI_RES16) ? ld16f(g.residual, ro, g.out_dtype) : reinterpret_cast<const float*>(g.residual)[ro];
+        }
+        const int64_t o = static_cast<int64_t>(m) * g.ldo + n;
+        if (g.out_dtype == APX_F32) reinterpret_cast<float*>(g.out)[o] = v;
+        else if (g.out_dtype == APX_F16) reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(v);
+        else reinterpret_cast<__nv_bfloat16*>(g.out)[o] = __float2bfloat16_rn(v);
+    };
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
         if (m >= g.M) continue;
+        if (epi == APX_EPI_GEGLU) {   // columns (2j, 2j+1) = (hidden, gate)
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const int n = n0 + tx * 4 + j;
+                if (n + 1 >= g.N) continue;
+                const float a = acc[i][j] + (g.bias ? g.bias[n] : 0.f), gt = acc[i][j + 1] + (g.bias ? g.bias[n + 1] : 0.f);
+                put(m, n >> 1, a * gelu_erf_f(gt));
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n >= g.N) continue;
             float v = acc[i][j];
             if (g.bias) v += g.bias[n];
-            if (g.epilogue == APX_EPI_GELU) v = gelu_erf_f(v);
-            if (g.residual) v += g.residual[static_cast<int64_t>(m) * g.ldr + n];
-            const int64_t o = static_cast<int64_t>(m) * g.ldo + n;
-            if (g.out_dtype == APX_F32) reinterpret_cast<float*>(g.out)[o] = v;
-            else if (g.out_dtype == APX_F16) reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(v);
-            else reinterpret_cast<__nv_bfloat16*>(g.out)[o] = __float2bfloat16_rn(v);
+            if (epi == APX_EPI_GELU) v = gelu_erf_f(v);
+            put(m, n, v);
         }
     }
 }

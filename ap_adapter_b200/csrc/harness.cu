@@ -289,7 +289,14 @@ int main(int argc, char** argv) {
     G("gemm_128x128x128_bf16_cpu", 128, 128, 128, APX_BF16, APX_F32, false, 0, false, true);
     G("gemm_300x320x320_f16_bias_cpu", 300, 320, 320, APX_F16, APX_F16, true, 0, false, true);
     G("gemm_200x192x256_bf16_gelu_res_cpu", 200, 192, 256, APX_BF16, APX_F32, true, 1, true, true);
+    G("gemm_100x64x1024_f16_bias_splitk8_cpu", 100, 64, 1024, APX_F16, APX_F16, true, 0, false, true);
+    G("gemm_130x128x512_bf16_gelu_res_splitk4_cpu", 130, 128, 512, APX_BF16, APX_F32, true, 1, true, true);
     G("gemm_2000x256x256_f16", 2000, 256, 256, APX_F16, APX_F16, false, 0, false, false);
+    G("gemm_2000x256x1024_f16_res_splitk4", 2000, 256, 1024, APX_F16, APX_F32, true, 0, true, false);
+    G("gemm_500x384x1536_f16_bias_splitk8", 500, 384, 1536, APX_F16, APX_F16, true, 0, false, false);
+    G("gemm_126x640x2560_bf16_bias_splitk8", 126, 640, 2560, APX_BF16, APX_BF16, true, 0, false, false);
+    G("gemm_126x1920x640_f16_splitk4", 126, 1920, 640, APX_F16, APX_F16, false, 0, false, false);
+    G("gemm_513x768x3072_f16_res_splitk4", 513, 768, 3072, APX_F16, APX_F32, true, 0, true, false);
     G("gemm_504x384x384_f16_bias", 504, 384, 384, APX_F16, APX_F16, true, 0, false, false);
     G("gemm_128x640x640_bf16_bias", 128, 640, 640, APX_BF16, APX_BF16, true, 0, false, false);
     G("gemm_16000x256x256_f16_bias", 16000, 256, 256, APX_F16, APX_F16, true, 0, false, false);

@@ -53,6 +53,9 @@ extern "C" {
 /* ---- epilogue flags for apx_linear -------------------------------------------------- */
 #define APX_EPI_NONE      0
 #define APX_EPI_GELU      1   /* exact erf GELU, applied after the bias                      */
+#define APX_EPI_GEGLU     2   /* adjacent column pairs (a, g) -> a * gelu_erf(g); `out` has N/2 columns (diffusers GEGLU with the
+                                 projection rows interleaved by the host: row 2i = hidden_i, row 2i+1 = gate_i)                 */
+#define APX_EPI_RES16     4   /* flag, OR-ed in: `residual` holds `out_dtype` (16-bit) elements instead of fp32              */
 
 /* ---- kernel families ---------------------------------------------------------------- */
 #define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; single site kernel when packed weights are given) */
@@ -71,7 +74,8 @@ uint64_t    apx_launch_count(void);
  * Y[M,N] = act(A[M,K] · W[N,K]^T + bias[N]) + residual[M,N]
  *   A, W      : `in_dtype` (APX_F16 | APX_BF16), row-major, K contiguous, lda/ldw in elements
  *   bias      : fp32[N] or NULL
- *   residual  : fp32[M,N] (ld = ldr) or NULL; may alias `out` when out_dtype == APX_F32
+ *   residual  : fp32[M,N] (ld = ldr) or NULL; may alias `out` when out_dtype == APX_F32; with APX_EPI_RES16 it is 16-bit
+ *               (`out_dtype`) and may alias a 16-bit `out`; with APX_EPI_GEGLU it is [M, N/2] like `out`
  *   out       : `out_dtype` (APX_F16 | APX_BF16 | APX_F32), ld = ldo
  * Requirements (tcgen05 path): K % 64 == 0, N % 64 == 0, 16-byte aligned rows.
  */

@@ -87,9 +87,10 @@ def test_encoder_matches_oracle_batch_and_bf16(sd):
     m16 = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd4, depth=4).cuda()
     rep = m16.audiomae(mel.unsqueeze(1).cuda(), no_mask=True, no_average=True)
     assert rel_err(rep, ref) < ENC_TOL
-    # clips are independent: clip 1 alone is bitwise what it is inside the batch
+    # clips are independent: clip 1 alone is what it is inside the batch (not bitwise: the GEMM picks its split-K factor from
+    # the grid size, so the fp32 summation order of a row differs between batch sizes)
     alone = m16.audiomae(mel[1:2].unsqueeze(1).cuda(), no_mask=True, no_average=True)
-    assert torch.equal(alone[0], rep[1])
+    assert rel_err(alone[0], rep[1]) < 1e-3
     mbf = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd4, depth=4).cuda().to(torch.bfloat16)
     emb = mbf(mel.cuda(), time_pool=2, freq_pool=2)[0]
     assert emb.dtype == torch.bfloat16

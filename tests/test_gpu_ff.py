@@ -1,0 +1,95 @@
+"""§8(f-2) neighbour of the hot path: the transformer block's GEGLU FeedForward + residual as two tcgen05 GEMMs with fused
+epilogues (APX_EPI_GEGLU, APX_EPI_RES16), against the unfused fp32 torch graph of the same module
+(diffusers FeedForward(activation_fn="geglu"), which AudioLDM2's BasicTransformerBlock ends with)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ap_adapter_b200 import _lib
+from ap_adapter_b200.unet import BasicTransformerBlock, FeedForward
+
+from gpu_util import TOL, rel_err, rounded
+
+pytestmark = pytest.mark.gpu
+
+
+def _ff_ref(ff: FeedForward, x: torch.Tensor, res: torch.Tensor, dtype) -> torch.Tensor:
+    """fp32 math on the 16-bit-rounded operands; the hidden activation is rounded to `dtype` like the kernel's output."""
+    w1, b1 = ff.net[0].proj.weight.float(), ff.net[0].proj.bias.float()
+    w2, b2 = ff.net[2].weight.float(), ff.net[2].bias.float()
+    a, gate = F.linear(x.float(), w1, b1).chunk(2, dim=-1)
+    hidden = rounded(a * F.gelu(gate), dtype)
+    return F.linear(hidden, w2, b2) + res.float()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dim,tokens", [(128, 4000), (256, 1000), (384, 250), (640, 77), (256, 1), (640, 8)])
+def test_fused_feedforward_matches_fp32(dim, tokens, dtype):
+    torch.manual_seed(dim + tokens)
+    ff = FeedForward(dim).eval().to("cuda", dtype)
+    x = torch.randn(2, tokens, dim, device="cuda", dtype=dtype)
+    res = torch.randn(2, tokens, dim, device="cuda", dtype=dtype)
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        assert ff.fused_ok(x)
+        y = ff.fused(x, res)
+    assert _lib.launch_count() - n0 == 2
+    assert y.shape == x.shape and y.dtype == dtype
+    assert rel_err(y, _ff_ref(ff, x, res, dtype)) < TOL[dtype]
+
+
+def test_geglu_epilogue_agrees_with_cuda_core_gemm():
+    """The same epilogue flags through the cross-check GEMM (APX_IMPL_SIMT)."""
+    torch.manual_seed(3)
+    a = torch.randn(300, 128, device="cuda", dtype=torch.float16)
+    w = torch.randn(512, 128, device="cuda", dtype=torch.float16) * 0.1
+    b = torch.randn(512, device="cuda")
+    r = torch.randn(300, 256, device="cuda", dtype=torch.float16)
+    y_tc = _lib.linear(a, w, b, residual=r, geglu=True)
+    lib = _lib.load()
+    prev = lib.apx_get_impl()
+    lib.apx_set_impl(1)
+    try:
+        y_simt = _lib.linear(a, w, b, residual=r, geglu=True)
+    finally:
+        lib.apx_set_impl(prev)
+    z = F.linear(a.float(), w.float(), b)
+    ref = z[:, 0::2] * F.gelu(z[:, 1::2]) + r.float()
+    assert rel_err(y_tc, ref) < 1e-3 and rel_err(y_simt, ref) < 1e-3
+
+
+def test_block_takes_fused_route_and_matches_unfused():
+    torch.manual_seed(5)
+    blk = BasicTransformerBlock(256, 4, 64, cross_attention_dim=None, double_self_attention=False).eval().half().cuda()
+    h = torch.randn(2, 500, 256, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        y = blk(h)
+        assert _lib.launch_count() - n0 == 2
+        FeedForward.use_fused = False
+        try:
+            y_ref = blk(h)
+        finally:
+            FeedForward.use_fused = True
+    assert rel_err(y, y_ref) < 2e-3
+    # grad mode keeps the differentiable torch graph
+    n0 = _lib.launch_count()
+    blk(h)
+    assert _lib.launch_count() == n0
+
+
+def test_repack_after_weight_update():
+    ff = FeedForward(128).eval().half().cuda()
+    x = torch.randn(1, 64, 128, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        y0 = ff.fused(x, x)
+        ff.net[0].proj.weight.mul_(0.5)
+        ff.net[0].proj.bias.mul_(0.5)
+        y1 = ff.fused(x, x)
+        FeedForward.use_fused = False
+        try:
+            ref = ff(x) + x
+        finally:
+            FeedForward.use_fused = True
+    assert not torch.equal(y0, y1)
+    assert rel_err(y1, ref) < 2e-3

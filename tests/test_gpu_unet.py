@@ -5,12 +5,18 @@ import torch
 from ap_adapter_b200 import _lib
 from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
 from ap_adapter_b200.pipeline import APAdapterDenoiser
-from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, FeedForward, build_attn_processors
 from oracle.ref_processors import OracleIPAttnProcessor2_0
 
 from gpu_util import rel_err
 
 pytestmark = pytest.mark.gpu
+
+
+def _fused_ff_count(unet) -> int:
+    with torch.no_grad():
+        return sum(m.fused_ok(torch.empty(1, m.net[2].out_features, device="cuda", dtype=torch.float16))
+                   for m in unet.modules() if isinstance(m, FeedForward))
 
 
 @pytest.fixture(scope="module")
@@ -37,14 +43,20 @@ def test_unet_step_matches_pytorch_processors(setup):
     kw = dict(encoder_hidden_states=inp["gpe"], encoder_hidden_states_1=inp["pe"], encoder_attention_mask_1=inp["mask"])
     with torch.no_grad():
         unet.set_attn_processor(dict(theirs))
-        y_ref = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
+        # the comparison graph is the stock one: torch FeedForward, torch processors with separate to_q / to_k / to_v GEMMs
+        ff_fused, FeedForward.use_fused, AttnProcessor2_0.fuse_projections = FeedForward.use_fused, False, False
+        try:
+            y_ref = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
+        finally:
+            FeedForward.use_fused, AttnProcessor2_0.fuse_projections = ff_fused, True
         unet.set_attn_processor(dict(ours))
         n0 = _lib.launch_count()
         y = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
         launched = _lib.launch_count() - n0
     # every adapter site went through libapx: the 10 C = 256 sites run the single site kernel, the 22 C = 384 / 640 sites
     # the three-kernel tcgen05 path; context caches / packed weights are built on first use
-    assert launched >= 10 + 22 * 3, launched
+    n_ff = _fused_ff_count(unet)
+    assert launched >= 10 + 22 * 3 + 2 * n_ff, launched
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
     assert rel_err(y, y_ref) < 1e-2
@@ -62,7 +74,9 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     assert rel_err(graphed, eager) < 2e-3
     # replays launch kernels without passing through the C ABI again: only the 2 warm-up steps + the capture are counted
     per_step = den._graph["apx_launches_per_step"]
-    assert per_step == 10 * 1 + 22 * 3          # site kernel at the C = 256 sites, three kernels at C = 384 / 640
+    # site kernel at the C = 256 sites, three kernels at C = 384 / 640, two GEMMs per GEGLU FeedForward
+    n_ff = _fused_ff_count(unet)
+    assert per_step == 10 * 1 + 22 * 3 + 2 * n_ff
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)
