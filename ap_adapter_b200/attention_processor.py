@@ -70,7 +70,15 @@ class AttnProcessor2_0(nn.Module):
             return query, key, value
         return query, attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)
 
-    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+    accepts_residual = True   # __call__ takes `residual_inout` (the restated transformer block passes its residual stream)
+
+    def _bias_f32(self, bo):
+        key = (bo._version, bo.data_ptr(), bo.dtype)
+        if getattr(self, "_bo", None) is None or self._bo[0] != key:
+            self._bo = (key, bo.detach().float().contiguous())
+        return self._bo[1]
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, residual_inout=None):
         residual = hidden_states
         if attn.spatial_norm is not None:
             hidden_states = attn.spatial_norm(hidden_states, temb)
@@ -101,13 +109,28 @@ class AttnProcessor2_0(nn.Module):
         hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
                                                        is_causal=False)
         hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
-        hidden_states = attn.to_out[0](hidden_states)
+        out_proj = attn.to_out[0]
+        if (residual_inout is not None and input_ndim == 3 and hidden_states.is_cuda and not torch.is_grad_enabled()
+                and hidden_states.dtype in (torch.float16, torch.bfloat16) and out_proj.weight.dtype == hidden_states.dtype
+                and not attn.residual_connection and attn.rescale_output_factor == 1.0
+                and out_proj.in_features % 64 == 0 and out_proj.out_features % 64 == 0
+                and residual_inout.dtype == hidden_states.dtype and residual_inout.shape[-1] == out_proj.out_features
+                and not (attn.to_out[1].training and attn.to_out[1].p > 0)):
+            # to_out + bias + the block's residual add in one tcgen05 GEMM (16-bit residual epilogue); a new tensor is returned
+            bias = self._bias_f32(out_proj.bias) if out_proj.bias is not None else None
+            res2 = residual_inout.reshape(-1, out_proj.out_features)
+            out = _lib.linear(hidden_states.reshape(-1, out_proj.in_features), out_proj.weight, bias,
+                              residual=res2 if res2.stride(1) == 1 else res2.contiguous())
+            return out.view(residual_inout.shape)
+        hidden_states = out_proj(hidden_states)
         hidden_states = attn.to_out[1](hidden_states)
         if input_ndim == 4:
             hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
         if attn.residual_connection:
             hidden_states = hidden_states + residual
-        return hidden_states / attn.rescale_output_factor
+        if attn.rescale_output_factor != 1.0:   # x / 1.0 is x bit for bit; skipping it drops one kernel per site
+            hidden_states = hidden_states / attn.rescale_output_factor
+        return hidden_states if residual_inout is None else hidden_states + residual_inout
 
 
 class _IPAttnSiteFn(torch.autograd.Function):
@@ -251,7 +274,11 @@ class IPAttnProcessor2_0(nn.Module):
         return cache
 
     # -- forward -----------------------------------------------------------------------------------------
-    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+    accepts_residual = True   # __call__ takes `residual_inout` (the restated transformer block passes its residual stream)
+    folds_in_place = True     # ... and adds the site's output into it in place
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 residual_inout=None):
         if scale != 1.0:
             warnings.warn("`scale` of IPAttnProcessor should be set by `set_ip_adapter_scale`.")
         if attention_mask is not None:
@@ -312,19 +339,28 @@ class IPAttnProcessor2_0(nn.Module):
                 hidden_states = hidden_states + residual
             if attn.rescale_output_factor != 1.0:
                 hidden_states = hidden_states / attn.rescale_output_factor
-            return hidden_states
+            return hidden_states if residual_inout is None else hidden_states + residual_inout
         cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
         wq, wo, wpack = self._site_weights(attn, heads, dtype)
         bo = attn.to_out[0].bias
         if bo is not None:
             bo = self._bias_f32(bo)
-        y = torch.empty_like(x)
         wsb = lib.apx_ipattn_workspace_bytes(bc, s, c)
         work = _lib.workspace(wsb, x.device, "ipattn")
+        # The block's residual add (h + attn2(norm2(h))) folded into the kernel: the site's output boxes are TMA-reduce-added
+        # into the residual stream (three-kernel shapes: 16-bit residual operand of the to_out GEMM), in place.
+        fold = (residual_inout is not None and input_ndim == 3 and not attn.residual_connection
+                and attn.rescale_output_factor == 1.0 and residual_inout.shape == x.shape and residual_inout.dtype == dtype
+                and residual_inout.is_contiguous() and residual_inout.device == x.device
+                and not (attn.to_out[1].training and attn.to_out[1].p > 0))
+        y = residual_inout if fold else torch.empty_like(x)
+        fn, fname = (lib.apx_ipattn_fwd_add, "apx_ipattn_fwd_add") if fold else (lib.apx_ipattn_fwd, "apx_ipattn_fwd")
         with torch.cuda.device(x.device):
-            _lib.check(lib.apx_ipattn_fwd(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(wpack), _lib.ptr(bo),
-                                          _lib.ptr(y), bc, s, c, heads, lt, la, float(self.scale), _lib.dtype_code(dtype),
-                                          _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_ipattn_fwd")
+            _lib.check(fn(_lib.ptr(x), _lib.ptr(wq), _lib.ptr(cache), _lib.ptr(wo), _lib.ptr(wpack), _lib.ptr(bo),
+                          _lib.ptr(y), bc, s, c, heads, lt, la, float(self.scale), _lib.dtype_code(dtype),
+                          _lib.ptr(work), wsb, _lib.stream_ptr()), fname)
+        if fold:
+            return y
         hidden_states = attn.to_out[1](y)  # dropout (p = 0)
         if input_ndim == 4:
             hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
@@ -332,7 +368,7 @@ class IPAttnProcessor2_0(nn.Module):
             hidden_states = hidden_states + residual
         if attn.rescale_output_factor != 1.0:
             hidden_states = hidden_states / attn.rescale_output_factor
-        return hidden_states
+        return hidden_states if residual_inout is None else hidden_states + residual_inout
 
     def _bias_f32(self, bo: torch.Tensor) -> torch.Tensor:
         """fp32 copy of the out-projection bias (the epilogue adds it to the fp32 accumulator), cached per version."""

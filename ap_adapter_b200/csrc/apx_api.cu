@@ -228,9 +228,9 @@ int apx_ipattn_fused_ok(int C, int H, int Lt, int La) {
     return ipattn_site_supported(C, H, Lt, La) ? 1 : 0;
 }
 
-int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
-                   void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
+                           void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
+                           size_t workspace_bytes, void* stream, bool accumulate) {
     APX_REQUIRE(X && cache && Y, APX_EINVAL, "apx_ipattn_fwd: null pointer");
     APX_REQUIRE(Bc > 0 && S > 0 && C > 0 && H > 0 && C % H == 0 && Lt >= 0 && La >= 0 && Lt + La > 0, APX_EINVAL,
                 "apx_ipattn_fwd: bad shape Bc=%d S=%d C=%d H=%d Lt=%d La=%d", Bc, S, C, H, Lt, La);
@@ -243,7 +243,7 @@ int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void*
         const PackLayout pl = pack_layout(C, H);
         if (pl.site_bytes && site_kernel_enabled() && ipattn_site_supported(C, H, Lt, La))
             return ipattn_site(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
-                               La, ap_scale, dtype, st);
+                               La, ap_scale, dtype, accumulate, st);
     }
 
     APX_REQUIRE(Wq && Wo && workspace, APX_EINVAL, "apx_ipattn_fwd: the three-kernel path needs Wq, Wo and a workspace");
@@ -267,7 +267,22 @@ int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void*
         rc = ipattn_core_tc(q, cb + lay.tiles_off, o, Bc, S, C, H, Lt, La, ap_scale, dtype, st);
     }
     if (rc) return rc;
-    return apx_linear(o, C, Wo, C, bo, nullptr, 0, Y, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
+    // accumulate: the residual stream in Y is the 16-bit residual operand of the to_out GEMM and is overwritten in place
+    return apx_linear(o, C, Wo, C, bo, accumulate ? static_cast<const float*>(Y) : nullptr, C, Y, C, M, C, C, dtype, dtype,
+                      accumulate ? APX_EPI_RES16 : APX_EPI_NONE, stream);
+}
+
+int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
+                   void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    return ipattn_fwd_impl(X, Wq, cache, Wo, wpack, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, workspace, workspace_bytes, stream,
+                           false);
+}
+int apx_ipattn_fwd_add(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
+                       void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    return ipattn_fwd_impl(X, Wq, cache, Wo, wpack, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, workspace, workspace_bytes, stream,
+                           true);
 }
 
 // ---- AudioMAE -----------------------------------------------------------------------------------

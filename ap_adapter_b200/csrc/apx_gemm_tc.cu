@@ -85,6 +85,9 @@ __device__ __forceinline__ void finish8(const GemmArgs& g, int row, int ocol, in
     }
     if (g.residual) {
         if (g.epilogue & APX_EPI_RES16) {
+            // the 16-bit residual is the caller's `y + h`: y is rounded to the output type first, then the sum is rounded once more
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) unpack16(pack16(v[i], v[i + 1], g.out_dtype), g.out_dtype, v[i], v[i + 1]);
             float lo, hi;
             unpack16(res.a.x, g.out_dtype, lo, hi); v[0] += lo; v[1] += hi;
             unpack16(res.a.y, g.out_dtype, lo, hi); v[2] += lo; v[3] += hi;
@@ -250,14 +253,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             nxt.a = make_uint4(0, 0, 0, 0); nxt.b = nxt.a;
             if (g.residual && rl + ROWS_STEP < rows_per && row + ROWS_STEP < g.M) nxt = load_res8(g, row + ROWS_STEP, ocol, nout);
             if (row < g.M) {
-                const float* own = sP + (row_base + rl) * LDT + cg * 8;
+                // partials are summed in rank order whatever z is, so a row's value does not depend on where in a tile it sits
                 float v[8];
-                const float4 a0 = *reinterpret_cast<const float4*>(own), a1 = *reinterpret_cast<const float4*>(own + 4);
-                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                for (int sl = 0; sl < splits - 1; ++sl) {
-                    const float* rp = sRecv + (sl * rows_per + rl) * LDT + cg * 8;
+                for (int p = 0; p < splits; ++p) {
+                    const float* rp = p == z ? sP + (row_base + rl) * LDT + cg * 8
+                                             : sRecv + ((p < z ? p : p - 1) * rows_per + rl) * LDT + cg * 8;
                     const float4 b0 = *reinterpret_cast<const float4*>(rp), b1 = *reinterpret_cast<const float4*>(rp + 4);
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    if (p == 0) {
+                        v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+                    } else {
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
                 }
                 finish8(g, row, ocol, nout, v, bias, cur);
             }

@@ -76,7 +76,7 @@ SiteGeom site_geom(int C, int H);
 bool ipattn_site_supported(int C, int H, int Lt, int La);
 int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
-                int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st);
+                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
 
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,

@@ -115,6 +115,7 @@ struct SiteArgs {
     int cs, hg, cn;                            // cluster size; heads and output columns per CTA (H / cs, C / cs)
     uint32_t off_p, off_k, off_v, off_bar;     // shared-memory offsets from the 1024-aligned base (sQO is at 0)
     uint32_t wo_off[4];                        // where each Wo stage lands
+    int accumulate;                            // 1: Y += result (TMA reduce-add into the residual stream), 0: Y = result
     long long* trace;                          // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0)
 };
 
@@ -653,7 +654,9 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 fence_proxy_async_smem();
                 named_bar_sync(3 + g, 128);
                 if (t0) {
-                    tma_store_3d(&tmY, sP + kb * X_CHUNK_BYTES, (kb0 + kb) * 64, m0, b);
+                    // accumulate: Y holds the block's residual stream, the box is added to it (one 16-bit rounding, as h + y)
+                    if (a.accumulate) tma_reduce_add_3d(&tmY, sP + kb * X_CHUNK_BYTES, (kb0 + kb) * 64, m0, b);
+                    else tma_store_3d(&tmY, sP + kb * X_CHUNK_BYTES, (kb0 + kb) * 64, m0, b);
                     tma_store_commit();
                 }
             }
@@ -749,7 +752,7 @@ int ipattn_site_pick_cluster(int Bc, int S, int C, int H) {
 }
 
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
-                int H, int Lt, int La, float ap_scale, int dtype, cudaStream_t st) {
+                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st) {
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site: dtype %d", dtype);
     int cs = ipattn_site_pick_cluster(Bc, S, C, H);
     const SiteGeom g = site_geom(C, H);
@@ -784,6 +787,7 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
     a.S = S; a.C = C; a.H = H; a.d_pad = g.d_pad; a.dv_pad = kg.dv_pad; a.Nq = g.Nq; a.n_kb = g.n_kb;
     a.Lt = Lt; a.La = La; a.Lt_pad = kg.Lt_pad; a.La_pad = kg.La_pad; a.L_pad = kg.L_pad;
     a.ap_scale = ap_scale;
+    a.accumulate = accumulate ? 1 : 0;
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(g.d));
     a.kv_bytes = static_cast<uint32_t>(kg.bytes_per_bh);
     a.k_tile_bytes = static_cast<uint32_t>(kg.k_tile_bytes);

@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g) {
     auto put = [&](int m, int n, float v) {   // n = OUTPUT column
         if (g.residual) {
             const int64_t ro = static_cast<int64_t>(m) * g.ldr + n;
-            v += (g.epilogue & APX_EPI_RES16) ? ld16f(g.residual, ro, g.out_dtype) : reinterpret_cast<const float*>(g.residual)[ro];
+            if (g.epilogue & APX_EPI_RES16) {   // y rounded to the output type, then y + h (see apx.h)
+                v = g.out_dtype == APX_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+                v += ld16f(g.residual, ro, g.out_dtype);
+            } else {
+                v += reinterpret_cast<const float*>(g.residual)[ro];
+            }
         }
         const int64_t o = static_cast<int64_t>(m) * g.ldo + n;
         if (g.out_dtype == APX_F32) reinterpret_cast<float*>(g.out)[o] = v;

@@ -136,6 +136,10 @@ class FeedForward(nn.Module):
 class BasicTransformerBlock(nn.Module):
     """norm1 -> attn1 -> +res; norm2 -> attn2(ctx) -> +res; norm3 -> GEGLU FF -> +res."""
 
+    # class-wide switch (APX_FOLD_RESIDUAL): "ip" (default) only the adapter sites, which add in place; "1" also the plain sites
+    # (to_out + residual through libapx's GEMM — measured 0.37 ms per step SLOWER than cuBLAS + add on B200, kept opt-in); "0" none
+    fold_residual = {"0": False, "1": True}.get(os.environ.get("APX_FOLD_RESIDUAL", "ip"), "ip")
+
     def __init__(self, dim: int, heads: int, dim_head: int, cross_attention_dim: Optional[int],
                  double_self_attention: bool = False, only_cross_attention: bool = False):
         super().__init__()
@@ -154,12 +158,24 @@ class BasicTransformerBlock(nn.Module):
     def forward(self, h, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 cross_attention_kwargs=None):
         kw = cross_attention_kwargs or {}
-        h = self.attn1(self.norm1(h), encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
-                       attention_mask=attention_mask, **kw) + h
+        # Inference on CUDA: processors that take `residual_inout` fold this block's residual add into their last kernel (the
+        # adapter sites add into h in place — h is this block's own tensor by then —, the plain sites return a new tensor).
+        fold = h.is_cuda and not torch.is_grad_enabled() and not h.requires_grad and self.fold_residual
+        x = self.norm1(h)
+        ehs1 = encoder_hidden_states if self.only_cross_attention else None
+        if fold is True and getattr(self.attn1.processor, "accepts_residual", False):
+            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, residual_inout=h, **kw)
+        else:
+            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, **kw) + h
         if self.attn2 is not None:
             # the adapter hot path: attn2's input is norm2(h), its output is residual-added right here
-            h = self.attn2(self.norm2(h), encoder_hidden_states=encoder_hidden_states,
-                           attention_mask=encoder_attention_mask, **kw) + h
+            x = self.norm2(h)
+            if fold and getattr(self.attn2.processor, "accepts_residual", False) and (
+                    fold is True or getattr(self.attn2.processor, "folds_in_place", False)):
+                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask,
+                               residual_inout=h.contiguous(), **kw)
+            else:
+                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask, **kw) + h
         x = self.norm3(h)
         if self.ff.fused_ok(x):
             return self.ff.fused(x, h)

@@ -47,7 +47,10 @@ def workload_config(batch: int, n_gpus: int) -> dict:
             "clips_per_gpu": batch, "cfg_batch_per_gpu": 2 * batch, "text_tokens": LT, "audio_tokens": LA,
             "t5_tokens": L_T5, "ap_scale": AP_SCALE, "guidance_scale": GUIDANCE, "ddim_steps": INFER_STEPS,
             "parallelism": f"clips sharded over {n_gpus} rank(s), no data-path collective, final all-gather of latents",
-            "l2": "per-step working set (1.4 GB of fp16 UNet weights) exceeds the 126 MB L2; no flush needed"}
+            "l2": "per-step working set (1.4 GB of fp16 UNet weights) exceeds the 126 MB L2; no flush needed",
+            "host_graph": "adapter sites: libapx (site kernel / 3-kernel form, residual add folded in); GEGLU FeedForwards: 2 libapx "
+                          "GEMMs with GEGLU / residual epilogues; plain attention sites: fused QKV (KV) projection on cuBLAS + cuDNN SDPA; "
+                          "everything else stock PyTorch ops; one CUDA graph per step"}
 
 
 def peaks() -> dict:

@@ -9,7 +9,7 @@
  * no allocation and no host synchronisation, and are CUDA-graph capturable.
  *
  * Reference interfaces replaced (paths relative to the AP-adapter repository):
- *   apx_ipattn_fwd        APadapter/ap_adapter/attention_processor.py:347-470
+ *   apx_ipattn_fwd(_add)  APadapter/ap_adapter/attention_processor.py:347-470
  *                         (IPAttnProcessor2_0.__call__: to_q, two SDPAs, scale-add, to_out)
  *   apx_ipattn_bwd        autograd of the same call in train_apadapter_v2.py:939-958 (accelerator.backward through the
  *                         processor: dX, d to_k_ip.weight, d to_v_ip.weight)
@@ -55,7 +55,8 @@ extern "C" {
 #define APX_EPI_GELU      1   /* exact erf GELU, applied after the bias                      */
 #define APX_EPI_GEGLU     2   /* adjacent column pairs (a, g) -> a * gelu_erf(g); `out` has N/2 columns (diffusers GEGLU with the
                                  projection rows interleaved by the host: row 2i = hidden_i, row 2i+1 = gate_i)                 */
-#define APX_EPI_RES16     4   /* flag, OR-ed in: `residual` holds `out_dtype` (16-bit) elements instead of fp32              */
+#define APX_EPI_RES16     4   /* flag, OR-ed in: `residual` holds `out_dtype` (16-bit) elements instead of fp32; the GEMM value is
+                                 rounded to `out_dtype` before the add, as a separate 16-bit `y + h` would                    */
 
 /* ---- kernel families ---------------------------------------------------------------- */
 #define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; single site kernel when packed weights are given) */
@@ -136,6 +137,15 @@ size_t apx_ipattn_workspace_bytes(int Bc, int S, int C);
 int apx_ipattn_fwd(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
                    void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
                    void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Same site with the transformer block's residual add folded in (the caller's `attn2(norm2(h)) + h`, diffusers
+ * BasicTransformerBlock as used by pipeline_audioldm2.py's UNet):  Y <- Y + site(X), Y holding the residual stream h on entry.
+ * The site's value is rounded to `dtype` and added to Y with one more `dtype` rounding, exactly as the caller's elementwise add
+ * would (fused kernel: TMA reduce-add of the output boxes; three-kernel form: 16-bit residual operand of the to_out GEMM).
+ */
+int apx_ipattn_fwd_add(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
+                       void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Backward of one adapter site for adapter-only training (train_apadapter_v2.py:892-979: only to_k_ip / to_v_ip train, the

@@ -63,14 +63,15 @@ def test_block_takes_fused_route_and_matches_unfused():
     blk = BasicTransformerBlock(256, 4, 64, cross_attention_dim=None, double_self_attention=False).eval().half().cuda()
     h = torch.randn(2, 500, 256, device="cuda", dtype=torch.float16)
     with torch.no_grad():
-        n0 = _lib.launch_count()
-        y = blk(h)
-        assert _lib.launch_count() - n0 == 2
-        FeedForward.use_fused = False
+        BasicTransformerBlock.fold_residual = True
         try:
+            n0 = _lib.launch_count()
+            y = blk(h)
+            assert _lib.launch_count() - n0 == 3       # attn1's to_out + residual GEMM (opt-in), the two FeedForward GEMMs
+            FeedForward.use_fused = BasicTransformerBlock.fold_residual = False
             y_ref = blk(h)
         finally:
-            FeedForward.use_fused = True
+            FeedForward.use_fused, BasicTransformerBlock.fold_residual = True, "ip"
     assert rel_err(y, y_ref) < 2e-3
     # grad mode keeps the differentiable torch graph
     n0 = _lib.launch_count()
@@ -93,3 +94,30 @@ def test_repack_after_weight_update():
             FeedForward.use_fused = True
     assert not torch.equal(y0, y1)
     assert rel_err(y1, ref) < 2e-3
+
+
+@pytest.mark.parametrize("c,heads,s,cross", [(256, 8, 1000, None), (384, 8, 252, 1024), (640, 8, 64, None)])
+def test_plain_site_folds_to_out_and_residual_into_one_gemm(c, heads, s, cross):
+    """AttnProcessor2_0 with `residual_inout`: to_out + bias + the block's residual add as one libapx GEMM (APX_EPI_RES16)
+    against the stock F.linear + elementwise add of the same processor (reference attention_processor.py:280-292 + the
+    caller's add)."""
+    from ap_adapter_b200.attention_processor import AttnProcessor2_0
+    from ap_adapter_b200.unet import Attention
+    torch.manual_seed(c)
+    attn = Attention(c, cross, heads, c // heads).half().cuda().eval()
+    attn.set_processor(AttnProcessor2_0())
+    x = torch.randn(2, s, c, device="cuda", dtype=torch.float16)
+    h = torch.randn(2, s, c, device="cuda", dtype=torch.float16)
+    ctx = None if cross is None else torch.randn(2, 16, cross, device="cuda", dtype=torch.float16)
+    with torch.no_grad():
+        want = attn(x, encoder_hidden_states=ctx) + h
+        n0 = _lib.launch_count()
+        h_before = h.clone()
+        got = attn(x, encoder_hidden_states=ctx, residual_inout=h)
+        assert _lib.launch_count() - n0 == 1
+    assert torch.equal(h, h_before) and got.data_ptr() != h.data_ptr()   # the plain sites do not write into the residual stream
+    assert rel_err(got, want) < 1e-3
+    # grad mode: same signature, stock kernels
+    n0 = _lib.launch_count()
+    got2 = attn(x, encoder_hidden_states=ctx, residual_inout=h)
+    assert _lib.launch_count() == n0 and rel_err(got2, want) < 1e-3

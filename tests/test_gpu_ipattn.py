@@ -103,7 +103,8 @@ def test_full_size_properties_batch8():
     assert torch.equal(y5, y5b)
     lin = (y1.float() - y0.float()) - 2 * (y5.float() - y0.float())
     assert lin.abs().max().item() < 4e-3 * y1.float().abs().max().item()
-    # batch element 3 alone == batch element 3 inside the batch, bit for bit
+    # batch element 3 alone == batch element 3 inside the batch, bit for bit (the context GEMMs pick the same split-K factor at
+    # both sizes and sum the partials in rank order, so a row's value does not depend on its position)
     sub = dict(case, x=case["x"][3:4], ctx=case["ctx"][3:4])
     assert torch.equal(run_site(sub, torch.float16, scale=0.5)[0], y5[3])
     # permuting the audio tokens only reorders a sum
@@ -262,3 +263,26 @@ def test_adapter_training_step_reduces_the_loss():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("c,heads,s", [(256, 8, 1000), (256, 8, 77), (384, 8, 252), (640, 8, 64)])
+def test_residual_folded_into_the_site_matches_separate_add(c, heads, s, dtype):
+    """apx_ipattn_fwd_add (§8f-2, "residual add -> epilogue"): h += site(norm2(h)) in place equals the caller's elementwise add of the
+    same site output, bit for bit (one 16-bit rounding of the site, one of the sum) — fused kernel (C=256) and three-kernel form."""
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from ap_adapter_b200.unet import Attention
+    torch.manual_seed(c + s)
+    attn = Attention(c, 768, heads, c // heads).to("cuda", dtype).eval()
+    proc = IPAttnProcessor2_0(hidden_size=c, cross_attention_dim=768, num_tokens=8, scale=0.5, name="t").to("cuda", dtype)
+    attn.set_processor(proc)
+    x = torch.randn(2, s, c, device="cuda", dtype=dtype)
+    h = torch.randn(2, s, c, device="cuda", dtype=dtype)
+    ctx = torch.randn(2, 8 + 128, 768, device="cuda", dtype=dtype)
+    with torch.no_grad():
+        y = attn(x, encoder_hidden_states=ctx)
+        want = y + h
+        h2 = h.clone()
+        got = attn(x, encoder_hidden_states=ctx, residual_inout=h2)
+    assert got.data_ptr() == h2.data_ptr()          # in place
+    assert torch.equal(got, want)

@@ -5,7 +5,7 @@ import torch
 from ap_adapter_b200 import _lib
 from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
 from ap_adapter_b200.pipeline import APAdapterDenoiser
-from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, FeedForward, build_attn_processors
+from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
 from oracle.ref_processors import OracleIPAttnProcessor2_0
 
 from gpu_util import rel_err
@@ -44,11 +44,12 @@ def test_unet_step_matches_pytorch_processors(setup):
     with torch.no_grad():
         unet.set_attn_processor(dict(theirs))
         # the comparison graph is the stock one: torch FeedForward, torch processors with separate to_q / to_k / to_v GEMMs
-        ff_fused, FeedForward.use_fused, AttnProcessor2_0.fuse_projections = FeedForward.use_fused, False, False
+        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
         try:
             y_ref = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
         finally:
-            FeedForward.use_fused, AttnProcessor2_0.fuse_projections = ff_fused, True
+            FeedForward.use_fused = AttnProcessor2_0.fuse_projections = True
+            BasicTransformerBlock.fold_residual = "ip"
         unet.set_attn_processor(dict(ours))
         n0 = _lib.launch_count()
         y = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
@@ -56,6 +57,8 @@ def test_unet_step_matches_pytorch_processors(setup):
     # every adapter site went through libapx: the 10 C = 256 sites run the single site kernel, the 22 C = 384 / 640 sites
     # the three-kernel tcgen05 path; context caches / packed weights are built on first use
     n_ff = _fused_ff_count(unet)
+    n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values())
+    assert n_ff == 128 and n_plain == 224
     assert launched >= 10 + 22 * 3 + 2 * n_ff, launched
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
@@ -74,9 +77,11 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     assert rel_err(graphed, eager) < 2e-3
     # replays launch kernels without passing through the C ABI again: only the 2 warm-up steps + the capture are counted
     per_step = den._graph["apx_launches_per_step"]
-    # site kernel at the C = 256 sites, three kernels at C = 384 / 640, two GEMMs per GEGLU FeedForward
+    # site kernel at the C = 256 sites, three kernels at C = 384 / 640, two GEMMs per GEGLU FeedForward (the plain sites' to_out +
+    # residual GEMM is opt-in, APX_FOLD_RESIDUAL=1)
     n_ff = _fused_ff_count(unet)
-    assert per_step == 10 * 1 + 22 * 3 + 2 * n_ff
+    n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values()) if BasicTransformerBlock.fold_residual is True else 0
+    assert per_step == 10 * 1 + 22 * 3 + 2 * n_ff + n_plain
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)

@@ -15,6 +15,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ipa
     tools/apx_harness site_2x1000x256_8+128 > gpurun_out/ncu_site_b1_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ipattn_site' -s 3 -c 1 -o gpurun_out/prof_site_b8_${TAG} -f \
     tools/apx_harness site_16x1000x256_8+128 > gpurun_out/ncu_site_b8_${TAG}.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc' -s 2 -c 1 -o gpurun_out/prof_gemm_splitk_${TAG} -f \
+    tools/apx_harness gemm_126x640x2560 > gpurun_out/ncu_gemm_splitk_${TAG}.log 2>&1
 if [ "${2:-}" = "full" ]; then
   echo "== ncu launch list (one eager denoise step)"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/launches_${TAG}.csv \
