@@ -120,7 +120,8 @@ class ClockSampler:
             ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
         except Exception:
             ident = str(device_index)
-        self.cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", ident]
+        # 200 ms period: at 50 ms the polling itself cost the device-timed loop ~4 % (13.9 vs 13.3 ms per step with / without it)
+        self.cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", ident]
 
     def __enter__(self):
         try:

@@ -196,3 +196,51 @@ def test_kaldi_mel_banks_match_torchaudio():
     ours = kaldi_mel_banks()
     assert ours.shape == (128, 257) and torch.all(ours[:, 256] == 0)
     assert (ours[:, :256] - ref).abs().max().item() < 5e-5
+
+
+def test_feedforward_geglu_weight_interleave_is_the_same_function():
+    """FeedForward._packed(): rows (hidden_i, gate_i) interleaved so that the GEMM epilogue's pairwise a * gelu(g) over adjacent
+    columns equals diffusers' GEGLU chunk(2) (the arithmetic of APX_EPI_GEGLU restated with torch ops on the packed weight)."""
+    import torch.nn.functional as F
+    from ap_adapter_b200.unet import FeedForward
+    torch.manual_seed(0)
+    ff = FeedForward(64).eval()
+    x = torch.randn(3, 10, 64)
+    w1, b1, b2 = ff._packed()
+    assert w1.shape == (512, 64) and b1.shape == (512,) and b1.dtype == torch.float32 and b2.shape == (64,)
+    z = F.linear(x, w1, b1)
+    hidden = z[..., 0::2] * F.gelu(z[..., 1::2])
+    got = F.linear(hidden, ff.net[2].weight, b2) + x
+    with torch.no_grad():
+        want = ff(x) + x
+    assert torch.allclose(got, want, atol=1e-5)
+    # CPU tensors / grad mode never take the libapx route; the cache follows in-place weight updates
+    assert not ff.fused_ok(x)
+    packed_before = ff._packed()[0]
+    with torch.no_grad():
+        ff.net[0].proj.weight.mul_(2.0)
+    assert ff._packed()[0] is not packed_before and torch.equal(ff._packed()[0][0::2], ff.net[0].proj.weight[:256])
+
+
+def test_plain_processor_projection_fusion_and_residual_argument_on_cpu():
+    """AttnProcessor2_0: the concatenated QKV / KV weight is rebuilt when a projection changes, and `residual_inout` on the stock
+    (CPU / grad) route is a plain add (reference attention_processor.py:199-294 plus the caller's residual add)."""
+    from ap_adapter_b200.attention_processor import AttnProcessor2_0
+    from ap_adapter_b200.unet import Attention
+    torch.manual_seed(1)
+    attn = Attention(64, None, 4, 16).eval()
+    proc = AttnProcessor2_0()
+    attn.set_processor(proc)
+    w = proc._cat_weight((attn.to_q, attn.to_k, attn.to_v))
+    assert w.shape == (192, 64) and torch.equal(w[64:128], attn.to_k.weight)
+    assert proc._cat_weight((attn.to_q, attn.to_k, attn.to_v)) is w
+    with torch.no_grad():
+        attn.to_k.weight.add_(1.0)
+    w2 = proc._cat_weight((attn.to_q, attn.to_k, attn.to_v))
+    assert w2 is not w and torch.equal(w2[64:128], attn.to_k.weight)
+    x, h = torch.randn(2, 9, 64), torch.randn(2, 9, 64)
+    with torch.no_grad():
+        y = attn(x)
+        q, k, v = proc._project(attn, x, x, True)          # CPU: three separate projections
+        assert torch.equal(q, attn.to_q(x)) and torch.equal(k, attn.to_k(x)) and torch.equal(v, attn.to_v(x))
+        assert torch.equal(attn(x, residual_inout=h), y + h)
