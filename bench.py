@@ -304,7 +304,8 @@ def run_ours(args) -> dict:
     b = args.batch
     torch.manual_seed(0)
     unet = AudioLDM2UNet2DConditionModel().eval().half().to(dev)
-    unet.set_attn_processor(build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device=dev, dtype=torch.float16))
+    ours = build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
+    unet.set_attn_processor(dict(ours))
     den = APAdapterDenoiser(unet)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     lat0 = torch.randn(b, *LAT_SHAPE, generator=g, device=dev, dtype=torch.float16)
@@ -394,12 +395,89 @@ def run_ours(args) -> dict:
     if rank == 0:
         out["roofline"] = site_roofline(b)
         out["audiomae"] = audiomae_timing()
+        try:   # the fair same-box comparison; informational, never allowed to break the bench line
+            out["torch_gpu"] = torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps=min(args.steps, 50))
+        except Exception as exc:  # noqa: BLE001
+            out["torch_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(b, steps=3, warmup=1, budget_s=25.0)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out if rank == 0 else None
+
+
+
+class _TorchIPAttnSite(torch.nn.Module):
+    """Bench-local PyTorch restatement of the reference adapter processor (attention_processor.py:347-470: to_q, SDPA over the
+    text tokens, SDPA over the audio tokens through to_k_ip / to_v_ip, h + scale * h_ip, to_out) used ONLY for the `torch_gpu`
+    comparison leg: the same UNet step with stock cuBLAS + SDPA kernels on the same GPU.  Never on the product path."""
+
+    def __init__(self, hidden_size, name=None, cross_attention_dim=None, num_tokens=4, scale=1.0, do_copy=False):
+        super().__init__()
+        self.num_tokens, self.scale = num_tokens, scale
+        self.to_k_ip = torch.nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+        self.to_v_ip = torch.nn.Linear(cross_attention_dim or hidden_size, hidden_size, bias=False)
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+        import torch.nn.functional as F
+        b, _, c = hidden_states.shape
+        h = attn.heads
+
+        def split(t):
+            return t.view(b, -1, h, c // h).transpose(1, 2)
+
+        q = split(attn.to_q(hidden_states))
+        e_t, e_a = encoder_hidden_states[:, :self.num_tokens], encoder_hidden_states[:, self.num_tokens:]
+        o = F.scaled_dot_product_attention(q, split(attn.to_k(e_t)), split(attn.to_v(e_t)))
+        o_ip = F.scaled_dot_product_attention(q, split(self.to_k_ip(e_a)), split(self.to_v_ip(e_a)))
+        o = (o + self.scale * o_ip).transpose(1, 2).reshape(b, -1, c)
+        return attn.to_out[1](attn.to_out[0](o))
+
+
+def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> dict:
+    """The same denoise step with the stock PyTorch graph on the same GPU: reference-algorithm processors (cuBLAS + SDPA, fp16),
+    unfused FeedForward / projections / residual adds, captured into a CUDA graph and timed exactly like the product step."""
+    from ap_adapter_b200.attention_processor import AttnProcessor2_0
+    from ap_adapter_b200.pipeline import APAdapterDenoiser
+    from ap_adapter_b200.unet import BasicTransformerBlock, FeedForward, build_attn_processors
+    saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual)
+    dev = lat0.device
+    try:
+        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
+        theirs = build_attn_processors(unet, _TorchIPAttnSite, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
+        for k, p in ours.items():
+            if hasattr(p, "to_k_ip"):
+                theirs[k].load_state_dict(p.state_dict())
+        unet.set_attn_processor(dict(theirs))
+        den = APAdapterDenoiser(unet)
+        with torch.no_grad():
+            graph = den._step_graph(lat0, gpe, pe, mask, GUIDANCE)
+            assert graph["apx_launches_per_step"] == 0
+
+            def step(i):
+                graph["t"].copy_(ts[i % INFER_STEPS])
+                graph["coef"].copy_(coefs[i % INFER_STEPS])
+                graph["graph"].replay()
+                graph["latents"].copy_(graph["out"])
+
+            graph["latents"].copy_(lat0)
+            for i in range(3):
+                step(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+        return {"value": lat0.shape[0] * 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps_timed": steps,
+                "what": "same step, stock PyTorch graph on the same GPU: reference-algorithm processors (cuBLAS + cuDNN SDPA, fp16), "
+                        "unfused FeedForward / projections / residual adds, one CUDA graph per step, device-timed"}
+    finally:
+        FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual = saved
+        unet.set_attn_processor(dict(ours))
 
 
 def run_reference(args) -> dict:

@@ -244,3 +244,19 @@ def test_plain_processor_projection_fusion_and_residual_argument_on_cpu():
         q, k, v = proc._project(attn, x, x, True)          # CPU: three separate projections
         assert torch.equal(q, attn.to_q(x)) and torch.equal(k, attn.to_k(x)) and torch.equal(v, attn.to_v(x))
         assert torch.equal(attn(x, residual_inout=h), y + h)
+
+
+def test_bench_torch_gpu_comparison_processor_is_the_reference_algorithm():
+    """bench.py's `torch_gpu` leg times a bench-local PyTorch restatement of the adapter processor; it must compute what the
+    oracle (pinned against the reference's own outputs) computes."""
+    import bench
+    from ap_adapter_b200.unet import Attention
+    from oracle.ref_processors import OracleIPAttnProcessor2_0
+    torch.manual_seed(2)
+    attn = Attention(64, 768, 4, 16).eval()
+    a = bench._TorchIPAttnSite(hidden_size=64, name="s", cross_attention_dim=768, num_tokens=8, scale=0.5)
+    b = OracleIPAttnProcessor2_0(hidden_size=64, name="s", cross_attention_dim=768, num_tokens=8, scale=0.5)
+    b.load_state_dict(a.state_dict())
+    x, ctx = torch.randn(2, 33, 64), torch.randn(2, 8 + 24, 768)
+    with torch.no_grad():
+        assert torch.allclose(a(attn, x, encoder_hidden_states=ctx), b(attn, x, encoder_hidden_states=ctx), atol=1e-5)
