@@ -53,10 +53,13 @@ class AttnProcessor2_0(nn.Module):
         self._cat = None
 
     def _cat_weight(self, mods):
-        key = tuple((m.weight._version, m.weight.data_ptr(), m.weight.dtype) for m in mods)
-        if self._cat is None or self._cat[0] != key:
-            self._cat = (key, torch.cat([m.weight.detach() for m in mods], dim=0).contiguous())
-        return self._cat[1]
+        # keyed on the weight tensors themselves (kept referenced, so an address cannot be recycled under the cache) + versions
+        ws = tuple(m.weight for m in mods)
+        key = tuple((w._version, w.data_ptr(), w.dtype) for w in ws)
+        c = self._cat
+        if c is None or c[0] != key or len(c[2]) != len(ws) or any(a is not b for a, b in zip(c[2], ws)):
+            c = self._cat = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous(), ws)
+        return c[1]
 
     def _project(self, attn, hidden_states, encoder_hidden_states, self_attention):
         """(query, key, value) as (B, L, C) tensors (possibly strided views of one fused projection)."""
@@ -74,9 +77,10 @@ class AttnProcessor2_0(nn.Module):
 
     def _bias_f32(self, bo):
         key = (bo._version, bo.data_ptr(), bo.dtype)
-        if getattr(self, "_bo", None) is None or self._bo[0] != key:
-            self._bo = (key, bo.detach().float().contiguous())
-        return self._bo[1]
+        c = getattr(self, "_bo", None)
+        if c is None or c[0] != key or c[2] is not bo:
+            c = self._bo = (key, bo.detach().float().contiguous(), bo)
+        return c[1]
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, residual_inout=None):
         residual = hidden_states

@@ -115,13 +115,17 @@ class FeedForward(nn.Module):
 
     def _packed(self):
         proj, out = self.net[0].proj, self.net[2]
-        key = (proj.weight._version, proj.weight.data_ptr(), out.weight._version, out.weight.data_ptr(), proj.weight.dtype)
-        if self._fused is None or self._fused[0] != key:
+        # keyed on the source tensors themselves (kept referenced, so an address cannot be recycled under the cache) + versions
+        src = (proj.weight, proj.bias, out.bias)
+        key = tuple((t._version, t.data_ptr(), t.dtype) for t in src)
+        c = self._fused
+        if c is None or c[0] != key or any(a is not b for a, b in zip(c[4], src)):
             inner = proj.weight.shape[0] // 2
-            w = torch.stack((proj.weight[:inner], proj.weight[inner:]), dim=1).reshape(2 * inner, -1).contiguous()
-            b = torch.stack((proj.bias[:inner], proj.bias[inner:]), dim=1).reshape(-1).float().contiguous()
-            self._fused = (key, w, b, out.bias.float().contiguous())
-        return self._fused[1:]
+            with torch.no_grad():
+                w = torch.stack((proj.weight[:inner], proj.weight[inner:]), dim=1).reshape(2 * inner, -1).contiguous()
+                b = torch.stack((proj.bias[:inner], proj.bias[inner:]), dim=1).reshape(-1).float().contiguous()
+                c = self._fused = (key, w, b, out.bias.float().contiguous(), src)
+        return c[1:4]
 
     def fused(self, x, residual):
         """ff(x) + residual on (..., dim) 16-bit CUDA tensors."""
