@@ -124,16 +124,39 @@ def stream_ptr() -> c_void_p:
 
 
 _workspaces: dict[tuple, torch.Tensor] = {}
+_ws_scope: dict | None = None   # set by workspace_scope(): scratch buffers owned by one CUDA graph
+
+
+class workspace_scope:
+    """While active, ``workspace()`` hands out buffers from ``owner`` (a dict kept by the caller) instead of the process-wide
+    per-stream table.  A CUDA-graph capture runs inside one: the scratch buffers are then allocated in THAT graph's pool, live
+    exactly as long as the graph state that owns the dict, and two graphs never bake in the same scratch pointer."""
+
+    def __init__(self, owner: dict):
+        self.owner = owner
+
+    def __enter__(self):
+        global _ws_scope
+        self.prev, _ws_scope = _ws_scope, self.owner
+        return self.owner
+
+    def __exit__(self, *exc):
+        global _ws_scope
+        _ws_scope = self.prev
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
-    """A grow-only scratch buffer per (device, stream, tag).  Kernels on one stream are serialised, so one
-    buffer per stream is race-free; nothing is allocated on the steady-state path (CUDA-graph friendly)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
-    buf = _workspaces.get(key)
+    """A grow-only scratch buffer per (device, stream, tag) — or per (device, tag) of the active ``workspace_scope``.  Kernels
+    on one stream are serialised, so one buffer per stream is race-free (one host thread per stream is assumed); nothing is
+    allocated on the steady-state path (CUDA-graph friendly)."""
+    if _ws_scope is not None:
+        table, key = _ws_scope, (device.index, tag)
+    else:
+        table, key = _workspaces, (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = table.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
+        table[key] = buf
     return buf
 
 

@@ -147,7 +147,9 @@ class _IPAttnSiteFn(torch.autograd.Function):
     def forward(ctx_, x, enc, wk_ip, wv_ip, proc, attn, heads, lt, la):
         lib = _lib.load()
         dtype = x.dtype
-        cache = proc._context_cache(attn, enc, heads, dtype)
+        # training: the adapter weights change every step, and optimisers that write through `.data` / their own kernels
+        # (8-bit Adam, fused Adam, EMA copies) do not bump `_version` — always rebuild the context K/V from the live weights
+        cache = proc._context_cache(attn, enc, heads, dtype, force=True)
         wq, wo, wpack = proc._site_weights(attn, heads, dtype)
         bo = attn.to_out[0].bias
         bo = proc._bias_f32(bo) if bo is not None else None
@@ -250,11 +252,13 @@ class IPAttnProcessor2_0(nn.Module):
         self._w_cache = (key, (wq, wo, pack), (wq_p, wo_p))
         return self._w_cache[1]
 
-    def _context_cache(self, attn, ctx: torch.Tensor, heads: int, dtype: torch.dtype) -> torch.Tensor:
+    def _context_cache(self, attn, ctx: torch.Tensor, heads: int, dtype: torch.dtype, force: bool = False) -> torch.Tensor:
+        """Packed K / V of the context (apx_ctx_kv), cached per (context, weights) identity + version.  In-place edits that do
+        not bump ``_version`` (``param.data`` writes, raw kernels, graph replays) need ``invalidate_cache()``; ``force`` rebuilds."""
         wk, wv = attn.to_k.weight, attn.to_v.weight
         wk_ip, wv_ip = self.to_k_ip.weight, self.to_v_ip.weight
         key = (self._tkey(ctx), self._tkey(wk), self._tkey(wv), self._tkey(wk_ip), self._tkey(wv_ip), heads, self.num_tokens)
-        if self._ctx_cache is not None and self._ctx_cache[0] == key:
+        if not force and self._ctx_cache is not None and self._ctx_cache[0] == key:
             return self._ctx_cache[1]
         lib = _lib.load()
         bc, l, dctx = ctx.shape

@@ -23,6 +23,12 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 int current_impl() { return g_impl.load(std::memory_order_relaxed); }
+bool first_use_on_device(std::atomic<uint64_t>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const uint64_t bit = 1ull << dev;
+    return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point: libapx.so has no link-time dependency
 // on libcuda.so, so it loads (and its symbols can be checked) on a machine without a driver.

@@ -357,11 +357,10 @@ static int attention_core_launch(const void* Q, int64_t q_bs, int64_t q_rs, cons
     a.q_manual = q_manual;
 
     dim3 grid(ceil_div(S, 128), H, Bc);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_mask{0};
+    if (first_use_on_device(attr_mask)) {
         APX_CUDA(cudaFuncSetAttribute(ipattn_core_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         APX_CUDA(cudaFuncSetAttribute(ipattn_core_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     if (g.d_pad <= 64) ipattn_core_kernel<256><<<grid, 128, smem, st>>>(tmQ, a);
     else               ipattn_core_kernel<512><<<grid, 128, smem, st>>>(tmQ, a);

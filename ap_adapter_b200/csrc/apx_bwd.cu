@@ -26,7 +26,7 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-constexpr int BWD_MAXJ = 9;    // keys per lane -> Lt + La <= 288
+constexpr int BWD_MAXJ = 17;   // keys per lane -> Lt + La <= 544 (the un-pooled AudioMAE grid: 8 + 512, train_apadapter_v2.py:445-446)
 
 struct BwdArgs {
     const uint16_t* Q;    // [Bc, S, C]
@@ -41,19 +41,20 @@ struct BwdArgs {
     int fmt, pitch;       // K / V row pitch in shared memory (16-bit elements)
 };
 
-// NJ = key groups of 32 a lane owns one key of (ceil(L / 32)), R = query rows per warp (4 warps per block).
+// NJ = key groups of 32 a lane owns one key of (ceil(L / 32)), R = query rows per warp (4 warps per block), NJC = key groups
+// whose dK_a / dV_a partial sums are held in registers at once in phase 2 (NJ = 17 walks its keys in chunks of 5 groups).
 // Phase 1, per row: recompute scores and probabilities (two softmax segments), write dq, and KEEP for the lane's keys the two
 // coefficients the K / V gradients need (tau * ds_j and ap * p_j, zero for text keys) in registers.
 // Phase 2, per 8-dim chunk of the head: dK_a[j, c] += sum_rows coef_k[row][j] * q[row][c] (same for dV_a with dO) accumulates
 // in REGISTERS over the warp's rows, is reduced over the block's warps in shared memory and flushed with one global atomic
 // per (key, dim) per block.  (The first version did one shared-memory atomic per key, dim AND row: 2.3 ms per call.)
-template <int NJ, int R>
+template <int NJ, int R, int NJC>
 __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     uint16_t* sK = reinterpret_cast<uint16_t*>(smem_bwd);
     uint16_t* sV = sK + static_cast<size_t>(a.L) * a.pitch;
     float* sq = reinterpret_cast<float*>(sV + static_cast<size_t>(a.L) * a.pitch);   // [4 warps][R][2][d]: q and dO of the warp's rows
-    float* sred = sq + 4 * R * 2 * a.d;                                               // [2][NJ * 32][8]: block reduction of one chunk
+    float* sred = sq + 4 * R * 2 * a.d;                                               // [2][NJC * 32][8]: block reduction of one chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
             dp[jj] = ds;
         }
         // dq = tau sum_j ds_j k_j : the ds of the row go through shared memory, then lanes own PAIRS of head dims
-        float* sds = sq + 4 * R * 2 * a.d + 2 * NJ * 32 * 8 + warp * NJ * 32;
+        float* sds = sq + 4 * R * 2 * a.d + 2 * NJC * 32 * 8 + warp * NJ * 32;
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) sds[jj * 32 + lane] = dp[jj];
         __syncwarp();
@@ -178,11 +179,13 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
     }
     __syncwarp();
 
-    // ---- phase 2: dK_a / dV_a, one 8-dim chunk of the head at a time
+    // ---- phase 2: dK_a / dV_a, one 8-dim chunk of the head and NJC key groups at a time
     for (int c0 = 0; c0 < a.d; c0 += 8) {
-        float ak[NJ][8], av[NJ][8];
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj)
+      for (int j0 = 0; j0 < NJ; j0 += NJC) {
+        float ak[NJC][8], av[NJC][8];
+#pragma unroll
+        for (int jj = 0; jj < NJC; ++jj)
 #pragma unroll
             for (int c = 0; c < 8; ++c) { ak[jj][c] = 0.f; av[jj][c] = 0.f; }
 #pragma unroll
@@ -194,35 +197,38 @@ __global__ void __launch_bounds__(128) ipattn_bwd_kernel(BwdArgs a) {
             const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
             const float dov[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj)
+            for (int jj = 0; jj < NJC; ++jj)
+                if (j0 + jj < NJ) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    ak[jj][c] = fmaf(ck[r][jj], qv[c], ak[jj][c]);
-                    av[jj][c] = fmaf(cv[r][jj], dov[c], av[jj][c]);
+                    for (int c = 0; c < 8; ++c) {
+                        ak[jj][c] = fmaf(ck[r][j0 + jj < NJ ? j0 + jj : 0], qv[c], ak[jj][c]);
+                        av[jj][c] = fmaf(cv[r][j0 + jj < NJ ? j0 + jj : 0], dov[c], av[jj][c]);
+                    }
                 }
         }
         // reduce over the 4 warps in shared memory, then one global atomic per (key, dim)
         __syncthreads();   // previous chunk's flush has finished reading sred
-        for (int i = threadIdx.x; i < 2 * NJ * 32 * 8; i += 128) sred[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * NJC * 32 * 8; i += 128) sred[i] = 0.f;
         __syncthreads();
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj)
+        for (int jj = 0; jj < NJC; ++jj)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 // [key][8]: the 8 dims of a key are contiguous; consecutive lanes = consecutive keys -> stride 8 words: 8-way
                 // bank conflict on plain stores, harmless for the few atomics left here
                 atomicAdd(&sred[(jj * 32 + lane) * 8 + c], ak[jj][c]);
-                atomicAdd(&sred[NJ * 32 * 8 + (jj * 32 + lane) * 8 + c], av[jj][c]);
+                atomicAdd(&sred[NJC * 32 * 8 + (jj * 32 + lane) * 8 + c], av[jj][c]);
             }
         __syncthreads();
-        for (int i = threadIdx.x; i < NJ * 32 * 8; i += 128) {
-            const int j = i / 8, c = i % 8;
+        for (int i = threadIdx.x; i < NJC * 32 * 8; i += 128) {
+            const int j = j0 * 32 + i / 8, c = i % 8;
             if (j >= a.Lt && j < a.L && c0 + c < a.d) {
                 const size_t g = (static_cast<size_t>(b) * a.La + (j - a.Lt)) * a.C + h * a.d + c0 + c;
                 atomicAdd(&a.dKa[g], sred[i]);
-                atomicAdd(&a.dVa[g], sred[NJ * 32 * 8 + i]);
+                atomicAdd(&a.dVa[g], sred[NJC * 32 * 8 + i]);
             }
         }
+      }
     }
 }
 
@@ -359,22 +365,18 @@ int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo
     if (p16 % 2 == 0) ++p16;
     a.pitch = p16 * 8;
     const int nj = ceil_div(L, 32);
-    const int njt = nj <= 1 ? 1 : nj <= 2 ? 2 : nj <= 5 ? 5 : 9;   // instantiated key-group counts
-    const int rows = njt <= 5 ? 8 : 4;                             // query rows per warp (register budget of the coefficient cache)
+    const int njt = nj <= 1 ? 1 : nj <= 2 ? 2 : nj <= 5 ? 5 : nj <= 9 ? 9 : 17;   // instantiated key-group counts
+    const int rows = njt <= 5 ? 8 : njt <= 9 ? 4 : 2;              // query rows per warp (register budget of the coefficient cache)
+    const int njc = njt <= 9 ? njt : 5;                            // key groups per phase-2 pass
     const size_t smem = static_cast<size_t>(L) * a.pitch * 2 * 2 + static_cast<size_t>(4) * rows * 2 * d * 4 +
-                        static_cast<size_t>(2) * njt * 32 * 8 * 4 + static_cast<size_t>(4) * njt * 32 * 4;
+                        static_cast<size_t>(2) * njc * 32 * 8 * 4 + static_cast<size_t>(4) * njt * 32 * 4;
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "apx_ipattn_bwd: context %d+%d at d=%d needs %zu B of shared memory", Lt, La, d, smem);
     typedef void (*BwdFn)(BwdArgs);
-    const BwdFn fn = njt == 1 ? ipattn_bwd_kernel<1, 8> : njt == 2 ? ipattn_bwd_kernel<2, 8> : njt == 5 ? ipattn_bwd_kernel<5, 8>
-                                                                                                          : ipattn_bwd_kernel<9, 4>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        APX_CUDA(cudaFuncSetAttribute(ipattn_bwd_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    static const BwdFn fns[5] = {ipattn_bwd_kernel<1, 8, 1>, ipattn_bwd_kernel<2, 8, 2>, ipattn_bwd_kernel<5, 8, 5>, ipattn_bwd_kernel<9, 4, 9>,
+                                 ipattn_bwd_kernel<17, 2, 5>};
+    const BwdFn fn = fns[njt == 1 ? 0 : njt == 2 ? 1 : njt == 5 ? 2 : njt == 9 ? 3 : 4];
+    for (int i = 0; i < 5; ++i)   // per-device attribute; cheap enough to set on every call (a static flag would be per-process)
+        APX_CUDA(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     fn<<<dim3(ceil_div(S, 4 * rows), H, Bc), 128, smem, st>>>(a);
     APX_LAUNCH_CHECK("ipattn_bwd_kernel");
     rc = apx_linear(ws + w.dQ, C, ws + w.wqT, C, nullptr, nullptr, 0, dX, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);

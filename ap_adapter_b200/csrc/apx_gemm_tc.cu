@@ -279,11 +279,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_mask{0};
+    if (first_use_on_device(attr_mask)) {
         APX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       GemmCfg<BN>::SMEM_BYTES + MAX_RECV_BYTES));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ceil_div(g.M, BM), g.N / BN, g.splits);

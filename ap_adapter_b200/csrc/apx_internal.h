@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "../../include/apx.h"
 
 namespace apx {
@@ -32,6 +33,10 @@ void count_launch(int n = 1);
             return ::apx::set_error(APX_ECUDA, "launch of %s failed: %s", (name), cudaGetErrorString(_e)); \
         ::apx::count_launch();                                                                         \
     } while (0)
+
+// cudaFuncSetAttribute is PER DEVICE: `mask` (one per call site) has one bit per device ordinal; true on the first call on the
+// current device (thread-safe; ordinals >= 64 simply set the attribute every time).
+bool first_use_on_device(std::atomic<uint64_t>& mask);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -819,13 +819,12 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
         {ipattn_site_kernel<0, 0, 0, false>, ipattn_site_kernel<0, 2, 1, false>, ipattn_site_kernel<0, 3, 1, false>, ipattn_site_kernel<0, 9, 1, false>},
         {ipattn_site_kernel<1, 0, 0, false>, ipattn_site_kernel<1, 2, 1, false>, ipattn_site_kernel<1, 3, 1, false>, ipattn_site_kernel<1, 9, 1, false>},
         {ipattn_site_kernel<0, 0, 0, true>, ipattn_site_kernel<0, 2, 1, true>, ipattn_site_kernel<0, 3, 1, true>, ipattn_site_kernel<0, 9, 1, true>}};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_mask{0};
+    if (first_use_on_device(attr_mask)) {
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 4; ++j)
                 APX_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(table[i][j]), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               227 * 1024));
-        attr_set = true;
     }
     const KernelFn fn = table[(trace_on && dtype == APX_F16) ? 2 : (dtype == APX_F16 ? 0 : 1)][variant];
     cudaLaunchConfig_t cfg;

@@ -438,10 +438,9 @@ int attention_simt(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int
                    B, S, H, d, L, L0, w0, w1, 1.0f / sqrtf(static_cast<float>(d)), dtype == APX_F16 ? 0 : 1, p16 * 8};
     const size_t smem = static_cast<size_t>(L) * a.pitch * 2 * 2 + 4 * d * sizeof(float);
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "attention: L=%d d=%d needs %zu B of shared memory", L, d, smem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_mask{0};
+    if (first_use_on_device(attr_mask)) {
         APX_CUDA(cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     dim3 grid(ceil_div(S, QPB), H, B);
     attention_simt_kernel<<<grid, 128, smem, st>>>(a);

@@ -159,11 +159,37 @@ class APAdapterDenoiser(nn.Module):
             g["latents"].copy_(g["out"])
         return g["latents"].clone()
 
+    def invalidate_graph(self):
+        """Drop the captured step graph (and the processors' context / weight caches it points into).  Needed only after edits
+        the cache keys cannot see: a context rewritten in place by a raw kernel or a captured graph, ``param.data`` writes."""
+        self._graph = None
+        for proc in self._adapter_procs():
+            proc.invalidate_cache()
+
+    def _adapter_procs(self):
+        procs = getattr(self.unet, "attn_processors", None)
+        if not isinstance(procs, dict):
+            return []
+        return [p for p in procs.values() if hasattr(p, "to_k_ip")]
+
+    def _site_state(self):
+        """Everything of the adapter sites a captured step bakes in besides the tensors in the key: ap_scale (a kernel argument),
+        num_tokens, and the identity / version of the trainable projections and of the UNet-side weights the caches are built from."""
+        out = []
+        for proc in self._adapter_procs():
+            ws = (proc.to_k_ip.weight, proc.to_v_ip.weight)
+            out.append((float(proc.scale), int(proc.num_tokens)) + tuple((w.data_ptr(), w._version, w.dtype) for w in ws))
+        return tuple(out)
+
     def _step_graph(self, latents, gpe, pe, mask, guidance_scale):
-        key = (tuple(latents.shape), latents.dtype, gpe.data_ptr(), gpe._version, pe.data_ptr(), pe._version,
-               None if mask is None else mask.data_ptr(), float(guidance_scale))
+        key = (tuple(latents.shape), latents.dtype, gpe.data_ptr(), gpe._version, tuple(gpe.shape), pe.data_ptr(), pe._version,
+               tuple(pe.shape), None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape)), float(guidance_scale),
+               self._site_state())
         if self._graph is not None and self._graph["key"] == key:
-            return self._graph
+            # the blobs the captured kernels read must still be the processors' current ones (an eager call with another
+            # context in between replaces them; the graph keeps its own alive through st["keep"], but then they are stale)
+            if all(a is b for a, b in zip(self._graph["blobs"], self._site_blobs())):
+                return self._graph
         dev = latents.device
         st = dict(key=key, latents=torch.zeros_like(latents), t=torch.zeros((), dtype=torch.int64, device=dev),
                   coef=torch.ones(4, dtype=torch.float32, device=dev), keep=(gpe, pe, mask))
@@ -176,18 +202,28 @@ class APAdapterDenoiser(nn.Module):
         from . import _lib
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
+        st["ws"] = {}   # this graph's own scratch buffers (allocated in its pool during the capture)
+        with _lib.workspace_scope(st["ws"]), torch.cuda.graph(graph):
             st["out"] = self.denoise_step(st["latents"], st["t"], st["coef"], gpe, pe, mask, guidance_scale)
         st["apx_launches_per_step"] = _lib.launch_count() - n0  # libapx kernels captured in one denoise step
         st["graph"] = graph
+        st["blobs"] = self._site_blobs()   # referenced here: the captured kernels hold raw pointers into them
         self._graph = st
         return st
+
+    def _site_blobs(self):
+        out = []
+        for proc in self._adapter_procs():
+            out.append(None if proc._ctx_cache is None else proc._ctx_cache[1])
+            out.append(None if proc._w_cache is None else proc._w_cache[1])
+        return out
 
     # ---- end to end (pipeline_audioldm2.py:748-1034, minus text encoders / VAE / vocoder) -------------------------------
     @torch.no_grad()
     def __call__(self, mel, prompt_embeds, attention_mask, generated_prompt_embeds, time_pooling: int = 2,
                  freq_pooling: int = 2, num_inference_steps: int = 200, guidance_scale: float = 3.5,
-                 audio_length_in_s: float = 10.0, generator=None, latents=None, use_cuda_graph: bool = True):
+                 audio_length_in_s: float = 10.0, generator=None, latents=None, use_cuda_graph: bool = True,
+                 steps_to_run: Optional[int] = None):
         """``prompt_embeds`` (2B, L_T5, 1024), ``attention_mask`` (2B, L_T5), ``generated_prompt_embeds`` (2B, 8, 768):
         the [negative; positive] outputs of ``encode_prompt`` (:902-915).  Returns the final latents (B, 8, T/4, 16)."""
         gpe = self.audio_condition(mel, generated_prompt_embeds, time_pooling, freq_pooling)
@@ -197,7 +233,7 @@ class APAdapterDenoiser(nn.Module):
             height = int(np.ceil(height / self.vae_scale_factor)) * self.vae_scale_factor
         latents = self.prepare_latents(batch, height, gpe.dtype, gpe.device, generator, latents)
         return self.denoise(latents, gpe, prompt_embeds.to(gpe.dtype), attention_mask, num_inference_steps,
-                            guidance_scale, use_cuda_graph)
+                            guidance_scale, use_cuda_graph, steps_to_run)
 
 
 # ---- batch sharding across ranks -------------------------------------------------------------------

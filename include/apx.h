@@ -152,7 +152,7 @@ int apx_ipattn_fwd_add(const void* X, const void* Wq, const void* cache, const v
  * UNet is frozen, and the loss must still reach the adapter sites further up, hence dX):
  *   dY, X, dX [Bc, S, C] `dtype`; Wq, Wo [C, C] `dtype` (as in apx_ipattn_fwd); `cache` = the context cache the forward used
  *   (apx_ctx_kv with the CURRENT adapter weights); ctx [Bc, Lt+La, Dctx] `dtype`; dWk_ip, dWv_ip fp32 [C, Dctx], overwritten.
- * Requires La > 0, Lt + La <= 288, d % 8 == 0, C % 64 == 0.
+ * Requires La > 0, Lt + La <= 544 (the un-pooled 8 + 512 context included), d % 8 == 0, C % 64 == 0.
  */
 size_t apx_ipattn_bwd_workspace_bytes(int Bc, int S, int C, int La);
 int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo, const void* cache, const void* ctx, void* dX,

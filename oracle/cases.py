@@ -13,12 +13,13 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 DCTX = 768
 
-# name -> (Bc, S, C, H, Lt(num_tokens), La, ap_scale, ctx_2d, real_ip_weights)
+# name -> (Bc, S, C, H, Lt(num_tokens), La, ap_scale, ctx_2d, real_ip_weights: False or the scale applied to them)
 IPATTN_CASES = {
     # BASELINE.json config 1: Q(2,1024,320), text-KV(2,77,768), audio-KV(2,8,768), ap_scale 0.5
     "cfg1":        (2, 1024, 320, 8, 77, 8, 0.5, False, False),
     # real site geometries, 10 s latent => S = 1000 / 252 / 64
-    "site256":     (2, 1000, 256, 8, 8, 128, 0.5, False, True),
+    "site256":     (2, 1000, 256, 8, 8, 128, 0.5, False, 8.0),    # shipped adapter-init weights x8 (sharp audio softmax)
+    "site256_real": (2, 1000, 256, 8, 8, 128, 0.5, False, 1.0),   # the same weights exactly as shipped
     "site384":     (2, 252, 384, 8, 8, 32, 0.55, False, False),
     "site640":     (2, 64, 640, 8, 8, 8, 0.5, False, False),
     "site256_la512": (1, 96, 256, 8, 8, 512, 1.0, False, False),
@@ -26,7 +27,7 @@ IPATTN_CASES = {
     "text_only":   (2, 33, 256, 8, 8, 0, 0.5, False, False),
 }
 # rows of the (Bc*S, C) output kept in the fixture (every k-th) to keep the files small
-ROW_STRIDE = {"cfg1": 8, "site256": 8}
+ROW_STRIDE = {"cfg1": 8, "site256": 8, "site256_real": 8}
 
 REAL_SITE = "down_blocks.1.attentions.1.transformer_blocks.0.attn2.processor"
 
@@ -53,8 +54,8 @@ def make_ipattn_case(name: str) -> dict:
     if real:
         # the shipped adapter-init weights (reference copied_cross_attention/*.bin), stored fp16 in the fixture
         f = np.load(os.path.join(GOLDEN_DIR, "real_ip_weights.npz"))
-        case["wk_ip"] = torch.from_numpy(f["k"].astype(np.float32)) * 8.0   # x8: keep the softmax non-trivial
-        case["wv_ip"] = torch.from_numpy(f["v"].astype(np.float32)) * 8.0
+        case["wk_ip"] = torch.from_numpy(f["k"].astype(np.float32)) * float(real)   # x8: a sharp softmax; x1: as shipped
+        case["wv_ip"] = torch.from_numpy(f["v"].astype(np.float32)) * float(real)
     return case
 
 

@@ -103,6 +103,24 @@ def gen_audiomae():
     np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "audiomae_reference.npz"), **out)
 
 
+def gen_frontend():
+    """Waveform fixtures for the GPU front-end (apx_resample / apx_fbank), made with the reference's own route
+    (audio_encoder/AudioMAE.py:356-366: torchaudio.functional.resample -> 16 kHz): the 16 kHz version of piano.wav that
+    ``mel_piano_f16`` in audiomae_reference.npz was computed from, and a 2 s excerpt at the original 48 kHz with its
+    reference-resampled counterpart."""
+    import torchaudio
+    from scipy.io import wavfile
+    sr, raw = wavfile.read(os.path.join(ref_shims.REF_ROOT, "piano.wav"))
+    assert sr == 48000 and raw.dtype == np.int16 and raw.ndim == 1
+    wav = torch.from_numpy(raw.astype(np.float32) / 32768.0).unsqueeze(0)
+    w16 = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=16000)
+    ex = raw[sr * 3: sr * 5]                                     # seconds 3..5
+    ex16 = torchaudio.functional.resample(torch.from_numpy(ex.astype(np.float32) / 32768.0).unsqueeze(0), orig_freq=sr, new_freq=16000)
+    np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "frontend_reference.npz"), piano16k=w16[0].numpy(), piano48k_2s_i16=ex,
+                        piano16k_2s=ex16[0].numpy(), sr=np.int64(sr))
+    print(f"frontend: piano16k {tuple(w16.shape)}, excerpt {ex.shape} -> {tuple(ex16.shape)}")
+
+
 def main():
     assert ref_shims.reference_available(), f"reference not found under {ref_shims.REF_ROOT}"
     os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
@@ -110,6 +128,7 @@ def main():
     gen_real_weights()
     gen_ipattn()
     gen_audiomae()
+    gen_frontend()
     for f in sorted(os.listdir(cases.GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(cases.GOLDEN_DIR, f)))
 

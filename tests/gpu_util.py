@@ -4,9 +4,40 @@ import torch
 from oracle import cases, ipattn_oracle, ref_shims
 
 # max|err| / max|ref| against the fp32 oracle fed with the SAME 16-bit-rounded operands.
-# north_star: "within 1e-3 relative (fp16/bf16)".  fp16 meets 1e-3.  bf16 stores 8 significand bits, so the output
-# rounding alone is 2^-9 = 2e-3 relative and the intermediate Q / P / O roundings add to it: 8e-3 is the bound there.
+# north_star: "within 1e-3 relative (fp16/bf16)".  fp16 meets 1e-3 against the fp32 oracle.  bf16 stores 8 significand bits:
+# the output rounding alone is 2^-9 = 2e-3 of the value, so NO bf16 implementation can sit within 1e-3 of an fp32 result; the
+# bar there is the reference's own bf16 path — the same algorithm run by stock PyTorch ops in bf16 on the same GPU
+# (`torch_lowp_site`): ours must be no further from the fp32 oracle than BF16_SLACK x that measured distance (see
+# `site_within_bar`), and every measured pair is written to gpurun_out/measured_errors.jsonl -> profiles/.
 TOL = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
+BF16_SLACK = 1.25
+
+
+def record(name: str, **vals):
+    """Append one measured-error record to gpurun_out/measured_errors.jsonl (best effort; the GPU box brings it back)."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "measured_errors.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()})) + "\n")
+    except OSError:
+        pass
+
+
+def site_within_bar(y, case, dtype, name="", scale=None):
+    """The parity bar of one adapter-site output.  fp16: max|err|/max|ref| < 1e-3 against the fp32 oracle.  bf16: no further
+    from the fp32 oracle than BF16_SLACK x the stock bf16 PyTorch path's own distance (and in any case < 8e-3)."""
+    ref = oracle_site(case, dtype, scale)
+    err = rel_err(y, ref)
+    if dtype == torch.float16:
+        record(name, dtype="f16", err=err, bar=TOL[dtype])
+        return err < TOL[dtype], (err,)
+    with torch.no_grad():
+        err_torch = rel_err(torch_lowp_site(case, dtype, scale), ref)
+    record(name, dtype="bf16", err=err, err_torch_bf16=err_torch, bar=max(1e-3, BF16_SLACK * err_torch))
+    return err < max(1e-3, BF16_SLACK * err_torch) and err < TOL[dtype], (err, err_torch)
 
 
 def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:

@@ -10,7 +10,7 @@ from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
 from oracle import audiomae_oracle as mae
 from oracle import cases
 
-from gpu_util import rel_err
+from gpu_util import record, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -71,7 +71,9 @@ def test_encoder_matches_reference_output_fixture(tag, model, gold):
     rep = model.audiomae(mel.unsqueeze(1).cuda(), no_mask=True, no_average=True)
     assert _lib.launch_count() - n0 >= 1 + 12 * 7 + 1
     assert rep.shape == (1, 513, 768)
-    assert rel_err(rep[0, ::8], torch.from_numpy(gold[f"{tag}_encoder_rows"])) < ENC_TOL
+    enc_err = rel_err(rep[0, ::8], torch.from_numpy(gold[f"{tag}_encoder_rows"]))
+    record(f"audiomae/encoder12_{tag}", err=enc_err, bar=ENC_TOL)
+    assert enc_err < ENC_TOL
     for tp, fp in cases.POOLS:
         emb, ones = model(mel.cuda(), time_pool=tp, freq_pool=fp)
         assert emb.shape == (1, 512 // (tp * fp), 768) and ones.shape == emb.shape[:2] and bool((ones == 1).all())
@@ -138,3 +140,17 @@ def test_fbank_front_end_matches_torchaudio(sr, seconds):
     got = extract_kaldi_fbank_feature(wav.cuda(), sr, torch.zeros(1024, 128))           # CUDA: libapx
     assert _lib.launch_count() - n0 == 2 and got.is_cuda and got.shape == (1024, 128)
     assert (got.cpu() - ref).abs().max().item() < 2e-3
+
+
+def test_fbank_front_end_matches_reference_generated_golden():
+    """apx_fbank on the 16 kHz piano.wav the reference's own ``extract_kaldi_fbank_feature`` (AudioMAE.py:356-394) turned into
+    ``mel_piano_f16`` (both fixtures written by oracle/gen_golden.py from /root/reference).  The golden is stored in fp16:
+    values are O(1), so its own quantisation is <= 1e-3; 3e-3 absolute covers that plus the DFT / log differences."""
+    from ap_adapter_b200.audiomae import extract_kaldi_fbank_feature
+
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "audiomae_reference.npz"))["mel_piano_f16"].astype(np.float32)
+    wav = torch.from_numpy(np.load(os.path.join(cases.GOLDEN_DIR, "frontend_reference.npz"))["piano16k"]).unsqueeze(0)
+    got = extract_kaldi_fbank_feature(wav.cuda(), 16000, torch.zeros(1024, 128))
+    err = (got.cpu() - torch.from_numpy(gold)).abs().max().item()
+    record("fbank/piano_vs_reference_golden", abs_err=err, bar=3e-3)
+    assert got.shape == (1024, 128) and err < 3e-3

@@ -9,7 +9,7 @@ import torch
 from ap_adapter_b200 import _lib
 from oracle import cases
 
-from gpu_util import TOL, build_site, oracle_site, random_site_case, rel_err, torch_lowp_site
+from gpu_util import TOL, build_site, oracle_site, random_site_case, record, rel_err, site_within_bar, torch_lowp_site
 
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float16, torch.bfloat16]
@@ -38,17 +38,20 @@ def test_site_matches_oracle(name, dtype):
     assert _lib.launch_count() > n0, "no libapx kernel was launched"
     ref = oracle_site(case, dtype)
     assert y.shape == ref.shape and y.dtype == dtype
-    err = rel_err(y, ref)
     if name == "site256":
         # The shipped adapter-init weights scaled x8 make the audio softmax sharp (logits of +-30): 16-bit rounding of Q and K
         # alone moves the output by more than 1e-3 — the reference's own PyTorch path in the same dtype (nn.Linear + SDPA on
         # this GPU) sits at the same distance from the fp32 oracle (1.56e-3 fp16 / 1.3e-2 bf16 measured).  The bar for this
-        # case is therefore "no further from the oracle than the stock 16-bit path", with 10 % slack for summation order.
+        # stress case is therefore "no further from the oracle than the stock 16-bit path", with 10 % slack for summation
+        # order.  The same weights exactly as shipped (`site256_real`) go through the plain bar below.
+        err = rel_err(y, ref)
         with torch.no_grad():
             err_torch = rel_err(torch_lowp_site(case, dtype), ref)
-        assert err < max(TOL[dtype], 1.1 * err_torch), (err, err_torch)
+        record("site_oracle/" + name, dtype=str(dtype), err=err, err_torch=err_torch)
+        assert err < max(1e-3, 1.1 * err_torch), (err, err_torch)
     else:
-        assert err < TOL[dtype]
+        ok, errs = site_within_bar(y, case, dtype, "site_oracle/" + name)
+        assert ok, errs
 
 
 @pytest.mark.parametrize("name", list(cases.IPATTN_CASES))
@@ -71,6 +74,10 @@ def test_site_matches_reference_output_fixture(name):
     (2, 100, 256, 8, 5, 0),      # no audio tokens
     (1, 200, 256, 8, 8, 512),    # un-pooled AudioMAE grid
     (2, 96, 512, 16, 8, 32),     # 16 heads, d = 32
+    (16, 252, 384, 8, 8, 128),   # BASELINE batch 8 (Bc = 16) at the C = 384 sites
+    (16, 64, 640, 8, 8, 128),    # ... and at the C = 640 sites
+    (4, 64, 640, 8, 8, 32),      # style_transfer preset (pool 4x4)
+    (8, 1000, 256, 8, 8, 8),     # pool 8x8
 ], ids=lambda s: "x".join(map(str, s)))
 def test_site_edge_shapes(shape):
     case = random_site_case(*shape, scale=0.7, seed=sum(shape))
@@ -209,7 +216,10 @@ def test_segmented_attention_kernel():
     (1, 130, 384, 8, 8, 128),    # three-kernel forward, d = 48, ragged query tile
     (2, 64, 640, 8, 8, 8),       # d = 80
     (1, 70, 256, 8, 0, 24),      # no text tokens
-], ids=["256_la32", "384_la128", "640_la8", "audio_only"])
+    (2, 150, 256, 8, 8, 512),    # un-pooled AudioMAE grid (pooling rate 1, drawn 25 % of the time: train_apadapter_v2.py:445-446)
+    (1, 100, 384, 8, 8, 512),
+    (2, 64, 640, 8, 8, 512),
+], ids=["256_la32", "384_la128", "640_la8", "audio_only", "256_la512", "384_la512", "640_la512"])
 def test_adapter_backward_matches_autograd_of_the_oracle(shape, dtype):
     """dX, d to_k_ip.weight, d to_v_ip.weight from apx_ipattn_bwd against torch autograd through the fp32 oracle evaluated on
     the same 16-bit-rounded operands, for a random upstream gradient.  Tolerance: max|err| / max|ref| <= 1e-2 (fp16) /
@@ -238,6 +248,8 @@ def test_adapter_backward_matches_autograd_of_the_oracle(shape, dtype):
     ref.backward(dy.to(dtype).float())
     assert rel_err(y, ref) < TOL[dtype]
     tol = 1e-2 if dtype == torch.float16 else 3e-2
+    record("site_bwd/" + "x".join(map(str, shape)), dtype=str(dtype), dx=rel_err(x.grad, xr.grad),
+           dwk=rel_err(proc.to_k_ip.weight.grad, wk_ip.grad), dwv=rel_err(proc.to_v_ip.weight.grad, wv_ip.grad), bar=tol)
     assert rel_err(x.grad, xr.grad) < tol
     assert rel_err(proc.to_k_ip.weight.grad, wk_ip.grad) < tol
     assert rel_err(proc.to_v_ip.weight.grad, wv_ip.grad) < tol

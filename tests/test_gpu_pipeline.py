@@ -1,0 +1,108 @@
+"""BASELINE config 3 as ONE path on the GPU: fbank-shaped mel -> libapx AudioMAE(mel) + AudioMAE(0) -> context concat ->
+context K/V caches -> CUDA-graphed CFG + DDIM steps, through ``APAdapterDenoiser.__call__`` (reference
+``pipeline/pipeline_audioldm2.py:919-1031``), against the same chain assembled from the oracle: ``oracle.audiomae_oracle``
+(fp32, CPU) for the two encodes and the oracle processors at every attention site of the same restated UNet."""
+import pytest
+import torch
+
+from ap_adapter_b200 import _lib
+from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
+from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
+from ap_adapter_b200.pipeline import APAdapterDenoiser
+from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
+from oracle import audiomae_oracle, cases
+from oracle.ref_processors import OracleIPAttnProcessor2_0
+
+from gpu_util import record, rel_err
+
+pytestmark = pytest.mark.gpu
+
+B, TP, FP, STEPS, GUIDANCE, AP_SCALE = 4, 2, 2, 3, 7.5, 0.5   # timbre_transfer preset (config.py:8-11), batch 4
+
+
+@pytest.fixture(scope="module")
+def world():
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval().half().cuda()
+    ours = build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device="cuda", dtype=torch.float16)
+    theirs = build_attn_processors(unet, OracleIPAttnProcessor2_0, AttnProcessor2_0, ap_scale=AP_SCALE, device="cuda", dtype=torch.float16)
+    for k, p in ours.items():
+        if hasattr(p, "to_k_ip"):
+            theirs[k].load_state_dict(p.state_dict())
+    sd = cases.mae_state_dict()                     # depth 12, numpy-seeded
+    mae = AudioMAEConditionCTPoolRand(checkpoint_path=None, state_dict=sd).cuda()
+    g = torch.Generator().manual_seed(5)
+    inputs = dict(mel=cases.make_mel(seed=9),       # (1, 1024, 128): one audio prompt for the whole batch (:919-933)
+                  gpe=torch.randn(2 * B, 8, 768, generator=g), pe=torch.randn(2 * B, 16, 1024, generator=g),
+                  mask=torch.ones(2 * B, 16), lat=torch.randn(B, 8, 250, 16, generator=g))
+    inputs["mask"][1, 9:] = 0
+    return unet, ours, theirs, mae, sd, inputs
+
+
+def test_config3_end_to_end_matches_the_oracle_chain(world):
+    unet, ours, theirs, mae, sd, inp = world
+    cu = lambda t: t.cuda()  # noqa: E731
+    # ---- product: one call (mel on the device -> final latents)
+    unet.set_attn_processor(dict(ours))
+    den = APAdapterDenoiser(unet, mae)
+    n0 = _lib.launch_count()
+    got = den(cu(inp["mel"]), cu(inp["pe"]).half(), cu(inp["mask"]), cu(inp["gpe"]).half(), time_pooling=TP, freq_pooling=FP,
+              num_inference_steps=200, guidance_scale=GUIDANCE, audio_length_in_s=10.0, latents=cu(inp["lat"]).half(),
+              steps_to_run=STEPS)
+    gpe_dev = den._graph["keep"][0]                              # the context the conditioning block built
+    assert gpe_dev.shape == (2 * B, 8 + 128, 768) and gpe_dev.dtype == torch.float16
+    assert _lib.launch_count() - n0 > 2 * (1 + 12 * 7 + 2)      # two AudioMAE encodes + the captured step
+    assert got.shape == (B, 8, 250, 16) and torch.isfinite(got).all()
+
+    # ---- oracle chain: fp32 CPU AudioMAE for cond / uncond, reference concat order, oracle processors, eager fp16 UNet
+    with torch.no_grad():
+        loa = audiomae_oracle.audiomae_forward(inp["mel"], sd, TP, FP)[0]
+        un = audiomae_oracle.audiomae_forward(torch.zeros_like(inp["mel"]), sd, TP, FP)[0]
+    neg_g, g = inp["gpe"].chunk(2)
+    ctx = torch.cat([torch.cat([neg_g, un.repeat(B, 1, 1)], 1), torch.cat([g, loa.repeat(B, 1, 1)], 1)], 0)
+    ctx_err = rel_err(gpe_dev, ctx)
+    record("config3/context", err=ctx_err)
+    assert ctx_err < 4e-3                                        # AudioMAE in fp16 GEMM operands + fp16 context storage
+    unet.set_attn_processor(dict(theirs))
+    FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
+    try:
+        ref_den = APAdapterDenoiser(unet)
+        want = ref_den.denoise(cu(inp["lat"]).half(), cu(ctx).half(), cu(inp["pe"]).half(), cu(inp["mask"]),
+                               num_inference_steps=200, guidance_scale=GUIDANCE, use_cuda_graph=False, steps_to_run=STEPS)
+    finally:
+        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = True
+        BasicTransformerBlock.fold_residual = "ip"
+        unet.set_attn_processor(dict(ours))
+    err = rel_err(got, want)
+    record("config3/latents_after_3_steps", err=err)
+    assert err < 1e-2
+
+
+def test_step_graph_follows_ap_scale_weights_and_context(world):
+    """The captured step bakes ap_scale, the context caches and the adapter weights in: changing any of them must re-capture."""
+    unet, ours, _, _, _, inp = world
+    unet.set_attn_processor(dict(ours))
+    den = APAdapterDenoiser(unet)
+    lat = inp["lat"][:1].cuda().half()
+    gpe = torch.randn(2, 8 + 32, 768, generator=torch.Generator().manual_seed(2)).cuda().half()
+    pe, mask = inp["pe"][:2].cuda().half(), inp["mask"][:2].cuda()
+    run = lambda: den.denoise(lat, gpe, pe, mask, num_inference_steps=200, guidance_scale=GUIDANCE, steps_to_run=2)  # noqa: E731
+    procs = [p for p in ours.values() if hasattr(p, "to_k_ip")]
+    a = run()
+    g0 = den._graph
+    assert run() is not None and den._graph is g0               # unchanged inputs: the same graph is replayed
+    for p in procs:
+        p.scale = 0.9
+    b = run()
+    assert den._graph is not g0 and not torch.equal(a, b)       # ap_scale sweep re-captures
+    eager = den.denoise(lat, gpe, pe, mask, num_inference_steps=200, guidance_scale=GUIDANCE, steps_to_run=2, use_cuda_graph=False)
+    assert rel_err(b, eager) < 2e-3
+    g1 = den._graph
+    with torch.no_grad():
+        procs[0].to_v_ip.weight.mul_(1.5)
+    c = run()
+    assert den._graph is not g1 and not torch.equal(b, c)       # weight update re-captures
+    for p in procs:
+        p.scale = AP_SCALE
+    with torch.no_grad():
+        procs[0].to_v_ip.weight.div_(1.5)

@@ -260,3 +260,59 @@ def test_bench_torch_gpu_comparison_processor_is_the_reference_algorithm():
     x, ctx = torch.randn(2, 33, 64), torch.randn(2, 8 + 24, 768)
     with torch.no_grad():
         assert torch.allclose(a(attn, x, encoder_hidden_states=ctx), b(attn, x, encoder_hidden_states=ctx), atol=1e-5)
+
+
+def test_audiomae_checkpoint_loader_reads_the_reference_format(tmp_path, monkeypatch):
+    """``pretrained.pth`` = ``{'model': state_dict}`` with timm key names, loaded non-strict from the working directory
+    (audio_encoder/AudioMAE.py:28-30): encoder keys land in the parameter tree, decoder / mask-token keys are ignored."""
+    from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand, Vanilla_AudioMAE
+    from ap_adapter_b200.weights import load_audiomae_checkpoint
+    from oracle import cases
+
+    sd = cases.mae_state_dict(depth=2)
+    full = dict(sd)
+    full["mask_token"] = torch.zeros(1, 1, 512)
+    full["decoder_embed.weight"] = torch.randn(512, 768)
+    full["decoder_blocks.0.attn.qkv.weight"] = torch.randn(1536, 512)
+    path = tmp_path / "pretrained.pth"
+    torch.save({"model": full, "epoch": 3}, path)
+    loaded = load_audiomae_checkpoint(str(path))
+    assert set(loaded) == set(sd) and all(torch.equal(loaded[k], sd[k]) for k in sd)
+    m = Vanilla_AudioMAE(checkpoint_path=str(path), depth=2)
+    got = m.model.state_dict()
+    assert set(got) == set(sd)
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    # the reference's default: a bare "pretrained.pth" resolved against the current directory
+    monkeypatch.chdir(tmp_path)
+    m2 = AudioMAEConditionCTPoolRand(depth=2)
+    assert torch.equal(m2.audiomae.model.blocks[1].mlp.fc2.weight, sd["blocks.1.mlp.fc2.weight"])
+    assert all(not p.requires_grad for p in m2.audiomae.parameters())
+    # a bare state dict (no 'model' wrapper) is accepted too
+    torch.save(full, tmp_path / "bare.pth")
+    assert set(load_audiomae_checkpoint(str(tmp_path / "bare.pth"))) == set(sd)
+    with pytest.raises(FileNotFoundError):
+        Vanilla_AudioMAE(checkpoint_path=str(tmp_path / "missing.pth"), depth=1)
+
+
+def test_step_graph_key_covers_what_a_captured_step_bakes_in(tiny_unet):
+    """APAdapterDenoiser._site_state: ap_scale, num_tokens and the adapter weights' identity / version are part of the graph key."""
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    procs = build_attn_processors(tiny_unet, IPAttnProcessor2_0, ap_scale=0.5)
+    tiny_unet.set_attn_processor(dict(procs))
+    den = APAdapterDenoiser(tiny_unet)
+    adapters = den._adapter_procs()
+    assert len(adapters) == sum(hasattr(p, "to_k_ip") for p in procs.values()) > 0
+    s0 = den._site_state()
+    assert den._site_state() == s0
+    adapters[0].scale = 0.75
+    s1 = den._site_state()
+    assert s1 != s0
+    with torch.no_grad():
+        adapters[-1].to_k_ip.weight.add_(1.0)
+    s2 = den._site_state()
+    assert s2 != s1
+    adapters[1].to_v_ip.weight = torch.nn.Parameter(torch.zeros_like(adapters[1].to_v_ip.weight))
+    assert den._site_state() != s2
+    assert den._site_blobs() == [None] * (2 * len(adapters))
+    den.invalidate_graph()
+    assert den._graph is None
