@@ -50,6 +50,8 @@ SYMBOLS = {
     "apx_ipattn_pack_bytes": (_Z, [_I, _I]),
     "apx_ipattn_pack": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "apx_ipattn_fused_ok": (_I, [_I, _I, _I, _I]),
+    "apx_ipattn_site_kernel": (_I, [_I, _I, _I, _I, _I, _I]),
+    "apx_set_site_variant": (_I, [_I]),
     "apx_ipattn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_ipattn_fwd_add": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_ipattn_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -200,22 +200,41 @@ size_t apx_ipattn_workspace_bytes(int Bc, int S, int C) {
     return 2 * align_up(static_cast<size_t>(Bc) * S * C * 2, 256);
 }
 
-// The pack blob holds the site kernel's re-layout of Wq / Wo (apx_ipattn_site.cu); shapes it does not cover take the
-// three-kernel path, which reads the weights as they are.  (The first-generation fused kernel, one head at a time, was
-// retired in round 1: at every shape it covered it was slower than the three-kernel path — profiles/r1_*.)
-struct PackLayout { size_t site_off, site_bytes, total; };
+// The pack blob holds the fused kernels' re-layouts of Wq / Wo: [all-heads kernel sections (apx_ipattn_site.cu)][one-head-per-CTA
+// kernel sections (apx_ipattn_h1.cu)]; shapes neither covers take the three-kernel path, which reads the weights as they are.
+struct PackLayout { size_t site_off, site_bytes, h1_off, h1_bytes, total; };
 static PackLayout pack_layout(int C, int H) {
     PackLayout l;
     const SiteGeom sg = site_geom(C, H);
+    const H1Geom hg = h1_geom(C, H);
     l.site_off = 0;
-    l.site_bytes = sg.ok ? sg.total : 0;
-    l.total = l.site_bytes;
+    l.site_bytes = sg.ok ? align_up(sg.total, 256) : 0;
+    l.h1_off = l.site_bytes;
+    l.h1_bytes = hg.ok ? align_up(hg.total, 256) : 0;
+    l.total = l.site_bytes + l.h1_bytes;
     return l;
 }
 // APX_SITE_KERNEL=0 forces the three-kernel path (A/B measurements only)
 static bool site_kernel_enabled() {
     static const bool on = [] { const char* e = getenv("APX_SITE_KERNEL"); return !(e && e[0] == '0'); }();
     return on;
+}
+static std::atomic<int> g_site_variant{[] { const char* e = getenv("APX_SITE_VARIANT"); return e ? atoi(e) : 0; }()};
+
+// Which fused kernel runs a site call: 0 = none (three kernels), 1 = all heads per CTA, 2 = one head per CTA (cluster of H).
+// The all-heads kernel issues N = 256 projections (tensor-efficient) but one CTA walks all heads of its tile: it wins once its
+// grid fills the machine; below that the one-head kernel spreads a tile over H SMs and wins on latency.
+static int pick_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
+    if (!site_kernel_enabled()) return 0;
+    const bool all_ok = site_geom(C, H).ok && ipattn_site_supported(C, H, Lt, La);
+    const bool h1_ok = ipattn_site_h1_supported(C, H, Lt, La);
+    const int forced = g_site_variant.load(std::memory_order_relaxed);
+    if (forced == APX_SITE_ALLHEADS) return all_ok ? 1 : 0;
+    if (forced == APX_SITE_ONEHEAD) return h1_ok ? 2 : 0;
+    if (!all_ok) return h1_ok ? 2 : 0;
+    if (!h1_ok) return 1;
+    const int tiles = ceil_div(S, 128) * Bc;
+    return tiles * H <= 148 ? 2 : 1;
 }
 
 size_t apx_ipattn_pack_bytes(int C, int H) {
@@ -227,11 +246,25 @@ int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, i
     APX_REQUIRE(C > 0 && H > 0 && C % H == 0, APX_EINVAL, "apx_ipattn_pack: bad shape C=%d H=%d", C, H);
     const PackLayout l = pack_layout(C, H);
     APX_REQUIRE(l.total > 0, APX_EUNSUPPORTED, "apx_ipattn_pack: no single-kernel path covers C=%d H=%d", C, H);
-    return ipattn_site_pack_weights(Wq, Wo, static_cast<uint8_t*>(wpack) + l.site_off, C, H, dtype, static_cast<cudaStream_t>(stream));
+    int rc = APX_OK;
+    if (l.site_bytes) rc = ipattn_site_pack_weights(Wq, Wo, static_cast<uint8_t*>(wpack) + l.site_off, C, H, dtype, static_cast<cudaStream_t>(stream));
+    if (rc == APX_OK && l.h1_bytes)
+        rc = ipattn_site_h1_pack_weights(Wq, Wo, static_cast<uint8_t*>(wpack) + l.h1_off, C, H, dtype, static_cast<cudaStream_t>(stream));
+    return rc;
 }
 int apx_ipattn_fused_ok(int C, int H, int Lt, int La) {
     if (C <= 0 || H <= 0 || C % H) return 0;
-    return ipattn_site_supported(C, H, Lt, La) ? 1 : 0;
+    return (ipattn_site_supported(C, H, Lt, La) || ipattn_site_h1_supported(C, H, Lt, La)) ? 1 : 0;
+}
+int apx_set_site_variant(int variant) {
+    APX_REQUIRE(variant == APX_SITE_AUTO || variant == APX_SITE_ALLHEADS || variant == APX_SITE_ONEHEAD, APX_EINVAL,
+                "apx_set_site_variant: unknown variant %d", variant);
+    g_site_variant.store(variant);
+    return APX_OK;
+}
+int apx_ipattn_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
+    if (Bc <= 0 || S <= 0 || C <= 0 || H <= 0 || C % H) return 0;
+    return pick_site_kernel(Bc, S, C, H, Lt, La);
 }
 
 static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
@@ -247,9 +280,13 @@ static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, con
     // the product path: one fused tcgen05 kernel per site
     if (current_impl() == APX_IMPL_TC && wpack) {
         const PackLayout pl = pack_layout(C, H);
-        if (pl.site_bytes && site_kernel_enabled() && ipattn_site_supported(C, H, Lt, La))
+        const int which = pick_site_kernel(Bc, S, C, H, Lt, La);
+        if (which == 1)
             return ipattn_site(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
                                La, ap_scale, dtype, accumulate, st);
+        if (which == 2)
+            return ipattn_site_h1(X, static_cast<const uint8_t*>(wpack) + pl.h1_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
+                                  La, ap_scale, dtype, accumulate, st);
     }
 
     APX_REQUIRE(Wq && Wo && workspace, APX_EINVAL, "apx_ipattn_fwd: the three-kernel path needs Wq, Wo and a workspace");

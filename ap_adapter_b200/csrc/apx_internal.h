@@ -83,6 +83,18 @@ int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, 
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
                 int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
 
+// ---- adapter site, one head per CTA + a cluster per query tile (apx_ipattn_h1.cu): any C = H * d with H <= 8 -------------------
+struct H1Geom {
+    int ok, C, H, d, d_pad, dv_pad, Nq, n_kb;
+    size_t wq_off, wo_off, total;       // weight-pack sections
+};
+H1Geom h1_geom(int C, int H);
+bool ipattn_site_h1_supported(int C, int H, int Lt, int La);
+int ipattn_site_h1_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
+int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C, int H,
+                   int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
+int ipattn_site_pick_cluster(int Bc, int S, int C, int H);
+
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
               int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,

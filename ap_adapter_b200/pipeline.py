@@ -164,13 +164,14 @@ class APAdapterDenoiser(nn.Module):
         the cache keys cannot see: a context rewritten in place by a raw kernel or a captured graph, ``param.data`` writes."""
         self._graph = None
         for proc in self._adapter_procs():
-            proc.invalidate_cache()
+            if hasattr(proc, "invalidate_cache"):
+                proc.invalidate_cache()
 
     def _adapter_procs(self):
         procs = getattr(self.unet, "attn_processors", None)
         if not isinstance(procs, dict):
             return []
-        return [p for p in procs.values() if hasattr(p, "to_k_ip")]
+        return [p for p in procs.values() if hasattr(p, "to_k_ip") and hasattr(p, "to_v_ip")]
 
     def _site_state(self):
         """Everything of the adapter sites a captured step bakes in besides the tensors in the key: ap_scale (a kernel argument),
@@ -178,7 +179,7 @@ class APAdapterDenoiser(nn.Module):
         out = []
         for proc in self._adapter_procs():
             ws = (proc.to_k_ip.weight, proc.to_v_ip.weight)
-            out.append((float(proc.scale), int(proc.num_tokens)) + tuple((w.data_ptr(), w._version, w.dtype) for w in ws))
+            out.append((float(proc.scale), int(getattr(proc, "num_tokens", 0))) + tuple((w.data_ptr(), w._version, w.dtype) for w in ws))
         return tuple(out)
 
     def _step_graph(self, latents, gpe, pe, mask, guidance_scale):
@@ -214,8 +215,9 @@ class APAdapterDenoiser(nn.Module):
     def _site_blobs(self):
         out = []
         for proc in self._adapter_procs():
-            out.append(None if proc._ctx_cache is None else proc._ctx_cache[1])
-            out.append(None if proc._w_cache is None else proc._w_cache[1])
+            ctx_c, w_c = getattr(proc, "_ctx_cache", None), getattr(proc, "_w_cache", None)   # libapx processors only
+            out.append(None if ctx_c is None else ctx_c[1])
+            out.append(None if w_c is None else w_c[1])
         return out
 
     # ---- end to end (pipeline_audioldm2.py:748-1034, minus text encoders / VAE / vocoder) -------------------------------

@@ -120,16 +120,24 @@ size_t apx_ctx_kv_workspace_bytes(int Bc, int Lt, int La, int C);
  */
 size_t apx_ipattn_pack_bytes(int C, int H);
 int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, int dtype, void* stream);
-/* 1 iff apx_ipattn_fwd runs this shape as the single fused kernel when given a pack */
+/* 1 iff apx_ipattn_fwd runs this (C, H, context) as ONE fused kernel when given a pack */
 int apx_ipattn_fused_ok(int C, int H, int Lt, int La);
+/* Which kernel apx_ipattn_fwd picks for a call with a pack: 0 = three kernels, 1 = all-heads site kernel (one CTA per 128-query
+ * tile: C <= 256), 2 = one-head-per-CTA site kernel (a cluster of H CTAs per tile: any C = H*d, H <= 8).  The choice between 1 and 2
+ * follows the grid size; apx_set_site_variant pins it (measurements / tests): APX_SITE_AUTO, _ALLHEADS, _ONEHEAD. */
+#define APX_SITE_AUTO      0
+#define APX_SITE_ALLHEADS  1
+#define APX_SITE_ONEHEAD   2
+int apx_ipattn_site_kernel(int Bc, int S, int C, int H, int Lt, int La);
+int apx_set_site_variant(int variant);
 
 /*
  * One adapter site, one denoise step (attention_processor.py:387-459):
  *   Y = ( SDPA(X Wq^T, K_t, V_t) + ap_scale · SDPA(X Wq^T, K_a, V_a) ) Wo^T + bo
  * X, Y [Bc, S, C] contiguous `dtype`; Wq, Wo [C, C] `dtype`; bo fp32[C] or NULL;
  * `cache` from apx_ctx_kv with identical (Bc, Lt, La, C, H); `wpack` from apx_ipattn_pack or NULL.
- * With a pack and a covered shape this is ONE tcgen05 kernel (to_q + both softmax(QK^T)V + ap_scale add + to_out);
- * otherwise three (GEMM, attention core, GEMM) using `workspace` for Q and O.  Wq / Wo may be NULL when the fused
+ * With a pack and a covered shape this is ONE tcgen05 kernel (to_q + both softmax(QK^T)V + ap_scale add + to_out; contexts of up to
+ * 256 padded tokens, H <= 8 or H*d_pad <= 256); otherwise three (GEMM, attention core, GEMM) using `workspace` for Q and O.  Wq / Wo may be NULL when the fused
  * kernel is guaranteed (apx_ipattn_fused_ok).
  * workspace: apx_ipattn_workspace_bytes(Bc, S, C) bytes.
  */

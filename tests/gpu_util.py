@@ -9,7 +9,7 @@ from oracle import cases, ipattn_oracle, ref_shims
 # bar there is the reference's own bf16 path — the same algorithm run by stock PyTorch ops in bf16 on the same GPU
 # (`torch_lowp_site`): ours must be no further from the fp32 oracle than BF16_SLACK x that measured distance (see
 # `site_within_bar`), and every measured pair is written to gpurun_out/measured_errors.jsonl -> profiles/.
-TOL = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
+TOL = {torch.float16: 1e-3, torch.bfloat16: 6e-3}   # bf16 cap: 1.25 x the largest stock-bf16 distance measured (profiles/r2a_measured_errors.jsonl: 4.7e-3)
 BF16_SLACK = 1.25
 
 
@@ -28,7 +28,7 @@ def record(name: str, **vals):
 
 def site_within_bar(y, case, dtype, name="", scale=None):
     """The parity bar of one adapter-site output.  fp16: max|err|/max|ref| < 1e-3 against the fp32 oracle.  bf16: no further
-    from the fp32 oracle than BF16_SLACK x the stock bf16 PyTorch path's own distance (and in any case < 8e-3)."""
+    from the fp32 oracle than BF16_SLACK x the stock bf16 PyTorch path's own distance (and in any case < 6e-3)."""
     ref = oracle_site(case, dtype, scale)
     err = rel_err(y, ref)
     if dtype == torch.float16:

@@ -222,8 +222,9 @@ def test_segmented_attention_kernel():
 ], ids=["256_la32", "384_la128", "640_la8", "audio_only", "256_la512", "384_la512", "640_la512"])
 def test_adapter_backward_matches_autograd_of_the_oracle(shape, dtype):
     """dX, d to_k_ip.weight, d to_v_ip.weight from apx_ipattn_bwd against torch autograd through the fp32 oracle evaluated on
-    the same 16-bit-rounded operands, for a random upstream gradient.  Tolerance: max|err| / max|ref| <= 1e-2 (fp16) /
-    3e-2 (bf16): the backward chains five 16-bit roundings (Q, dO, P recomputed from 16-bit K, dQ, dX)."""
+    the same 16-bit-rounded operands, for a random upstream gradient.  The backward chains five 16-bit roundings (Q, dO, P
+    recomputed from 16-bit K, dQ, dX); measured max over the seven shapes: 9.4e-4 (fp16) / 6.1e-3 (bf16)
+    (profiles/r2a_measured_errors.jsonl) -> the bar is 2x that: 2e-3 / 1.2e-2."""
     from oracle import ipattn_oracle
 
     bc, s, c, h, lt, la = shape
@@ -247,7 +248,7 @@ def test_adapter_backward_matches_autograd_of_the_oracle(shape, dtype):
     ref = ipattn_oracle.ipattn_forward(xr, r("ctx"), r("wq"), r("wk"), r("wv"), wk_ip, wv_ip, r("wo"), r("bo"), h, lt, 1.0)
     ref.backward(dy.to(dtype).float())
     assert rel_err(y, ref) < TOL[dtype]
-    tol = 1e-2 if dtype == torch.float16 else 3e-2
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
     record("site_bwd/" + "x".join(map(str, shape)), dtype=str(dtype), dx=rel_err(x.grad, xr.grad),
            dwk=rel_err(proc.to_k_ip.weight.grad, wk_ip.grad), dwv=rel_err(proc.to_v_ip.weight.grad, wv_ip.grad), bar=tol)
     assert rel_err(x.grad, xr.grad) < tol

@@ -62,7 +62,7 @@ def test_config3_end_to_end_matches_the_oracle_chain(world):
     ctx = torch.cat([torch.cat([neg_g, un.repeat(B, 1, 1)], 1), torch.cat([g, loa.repeat(B, 1, 1)], 1)], 0)
     ctx_err = rel_err(gpe_dev, ctx)
     record("config3/context", err=ctx_err)
-    assert ctx_err < 4e-3                                        # AudioMAE in fp16 GEMM operands + fp16 context storage
+    assert ctx_err < 1.5e-3                                      # AudioMAE with fp16 GEMM operands + fp16 context storage (measured 5.5e-4)
     unet.set_attn_processor(dict(theirs))
     FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
     try:
@@ -75,7 +75,7 @@ def test_config3_end_to_end_matches_the_oracle_chain(world):
         unet.set_attn_processor(dict(ours))
     err = rel_err(got, want)
     record("config3/latents_after_3_steps", err=err)
-    assert err < 1e-2
+    assert err < 4e-3                                            # measured 1.1e-3: three fp16 UNet evaluations apart only in the 32 sites
 
 
 def test_step_graph_follows_ap_scale_weights_and_context(world):
