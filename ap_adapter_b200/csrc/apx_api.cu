@@ -222,8 +222,14 @@ static bool site_kernel_enabled() {
 static std::atomic<int> g_site_variant{[] { const char* e = getenv("APX_SITE_VARIANT"); return e ? atoi(e) : 0; }()};
 
 // Which fused kernel runs a site call: 0 = none (three kernels), 1 = all heads per CTA, 2 = one head per CTA (cluster of H).
-// The all-heads kernel issues N = 256 projections (tensor-efficient) but one CTA walks all heads of its tile: it wins once its
-// grid fills the machine; below that the one-head kernel spreads a tile over H SMs and wins on latency.
+// Measured on B200 (profiles/r2d_harness_sites.txt, us per call, CUDA-graph replay):
+//   C=256 (2x1000, La=128): all-heads 12.6, one-head 27.3, three kernels 18.7     C=256 x16: 21.2 / 125 / 47
+//   C=384 (2x252):          one-head 18.6, three kernels 19.4                      C=384 x16: 51 / 24.7
+//   C=640 (2x64):           one-head 26.0, three kernels 18.8                      C=640 x16: 49 / 22.8
+//   C=192, H=4 (1x100):     one-head 13.1, three kernels 19.1       C=256, La=200 (2x300): one-head 17.1, three kernels 20.9
+// The all-heads kernel wins wherever it applies.  The one-head kernel pays for its decomposition — every CTA of a cluster streams
+// the whole X tile, and the O all-gather runs at ~17 B/clk per SM over distributed shared memory — so it is picked only where the
+// all-heads kernel does not apply, the gather is small (<= 90 KB per CTA) and the grid is a handful of clusters.
 static int pick_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
     if (!site_kernel_enabled()) return 0;
     const bool all_ok = site_geom(C, H).ok && ipattn_site_supported(C, H, Lt, La);
@@ -231,10 +237,12 @@ static int pick_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
     const int forced = g_site_variant.load(std::memory_order_relaxed);
     if (forced == APX_SITE_ALLHEADS) return all_ok ? 1 : 0;
     if (forced == APX_SITE_ONEHEAD) return h1_ok ? 2 : 0;
-    if (!all_ok) return h1_ok ? 2 : 0;
-    if (!h1_ok) return 1;
+    if (all_ok) return 1;
+    if (!h1_ok) return 0;
+    const H1Geom g = h1_geom(C, H);
     const int tiles = ceil_div(S, 128) * Bc;
-    return tiles * H <= 148 ? 2 : 1;
+    const size_t gather = static_cast<size_t>(H - 1) * g.d_pad * 256;
+    return (tiles * H <= 32 && gather <= 90 * 1024) ? 2 : 0;
 }
 
 size_t apx_ipattn_pack_bytes(int C, int H) {

@@ -19,8 +19,10 @@
 //             through a second ring; the d valid columns leave as ONE 4-D tensor-TMA store (or reduce-add into the residual stream)
 //
 // so any C = H * d with H <= 8 (the portable cluster size), d % 8 == 0 is covered: C = 256 / 320 / 384 / 640 of AudioLDM2
-//  with d = 32 / 40 / 48 / 80.  Shared memory: the O tile region (H*d_pad*256 B) is also the landing
-// zone of the phase-A ring and (when a half of it is large enough) of the P tile; K / V^T tiles and one Wo stage sit behind it.
+//  with d = 32 / 40 / 48 / 80.  Shared memory, two plans (h1_plan): when everything fits side by side
+// (C <= 384) the O tile region is ONLY ever written by its owner and by the peers' pushes, so a CTA pushes its slot the moment it
+// exists; at C = 640 the O tile region (160 KB) is also the landing zone of the phase-A ring and of the P tile, and a second
+// cluster barrier ("every CTA is past phase B") gates the pushes.
 //
 // Warp roles (192 threads): warps 0-3 = softmax / conversion / epilogue warpgroup (TMEM lane quarter = warp), warp 4 = TMEM
 // allocator + single-thread MMA issuer, warp 5 = TMA producer.
@@ -28,6 +30,7 @@
 #include "apx_ptx.cuh"
 #include "apx_site_common.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -53,7 +56,7 @@ H1Geom h1_geom(int C, int H) {
 namespace {
 
 constexpr int X_CHUNK_BYTES = 128 * 64 * 2;   // one SWIZZLE_128B box: 128 rows x 64 channels
-constexpr int KS = 4;                         // k-steps (16 O columns each) per Wo stage
+constexpr int KS = 8;                         // k-steps (16 O columns each) per Wo stage
 constexpr int NTHREADS = 192;
 constexpr int MAX_A = 6, MAX_W = 8;
 
@@ -93,11 +96,18 @@ struct H1Args {
     float ap_scale, scale_log2;
     uint32_t kv_bytes, k_tile_bytes, v_tile_bytes, vx_off, wq_chunk_bytes, wo_stage_bytes, a_stage_bytes, p_bytes, slot_bytes;
     int ns_a, n_w, nw_slots, wo_early, n_ko;
-    int p_in_r0;
-    uint32_t off_p, off_k, off_v, off_bar;     // shared-memory offsets from the 1024-aligned base (the O tile is at 0)
+    int p_in_r0, overlay;                      // overlay: phase-A ring / P tile share the O tile region -> pushes gated by cluster barrier #2
+    uint32_t off_a, off_p, off_k, off_v, off_bar;   // shared-memory offsets from the 1024-aligned base (the O tile is at 0)
     uint32_t wo_off[MAX_W];
     int accumulate;
+    long long* trace;      // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0); null on the product path
 };
+
+// trace slots: [0,16) MMA thread, [16,24) producer, [24,48) warpgroup thread 0
+#define H1_T(slot)                                                                      \
+    do {                                                                                \
+        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0) a.trace[(slot)] = clock64(); \
+    } while (0)
 
 enum {  // mbarrier slots
     B_A_FULL = 0, B_A_EMPTY = MAX_A, B_W_FULL = 2 * MAX_A, B_W_EMPTY = 2 * MAX_A + MAX_W, B_K_FULL = 2 * MAX_A + 2 * MAX_W, B_V_FULL,
@@ -155,75 +165,109 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     // tensor memory: Q accumulator, then S, then Y at column 0; {O_t, O_a} (dv_pad columns each, column d_pad = row sum) behind S
     const uint32_t tmem_O = tmem_base + a.L_pad;
+    const int first_wave = min(a.ns_a, a.n_kb);
+    const uint8_t* wq_src = a.wq + static_cast<size_t>(h) * a.n_kb * a.wq_chunk_bytes;
+    // one phase-A chunk (64 input channels): X box + the head's Wq rows -> ring slot kb % ns_a
+    auto load_a = [&](int kb) {
+        const int slot = kb % a.ns_a;
+        uint8_t* dst = smem + a.off_a + slot * a.a_stage_bytes;
+        mbar_expect_tx(&bars[B_A_FULL + slot], X_CHUNK_BYTES + a.wq_chunk_bytes);
+        tma_load_3d(dst, &tmX, kb * 64, m0, b, &bars[B_A_FULL + slot]);
+        tma_load_1d(dst + X_CHUNK_BYTES, wq_src + static_cast<size_t>(kb) * a.wq_chunk_bytes, a.wq_chunk_bytes, &bars[B_A_FULL + slot]);
+    };
 
     if (warp == 5) {
         // ================================================================ TMA producer (one thread)
+        const uint8_t* wo_src = a.wo + static_cast<size_t>(h) * a.n_ko * (a.wo_stage_bytes / KS);
+        auto load_wo = [&](int i) {
+            const int slot = i % a.nw_slots;
+            if (i >= a.nw_slots) mbar_wait_nocall(&bars[B_W_EMPTY + slot], ((i / a.nw_slots) - 1) & 1);
+            const int ks = min(KS, a.n_ko - i * KS);
+            const uint32_t bytes = ks * (a.wo_stage_bytes / KS);
+            mbar_expect_tx(&bars[B_W_FULL + slot], bytes);
+            tma_load_1d(smem + a.wo_off[slot], wo_src + static_cast<size_t>(i) * a.wo_stage_bytes, bytes, &bars[B_W_FULL + slot]);
+        };
         if (elect_one()) {
-            const uint8_t* wq_src = a.wq + static_cast<size_t>(h) * a.n_kb * a.wq_chunk_bytes;
-            const uint8_t* wo_src = a.wo + static_cast<size_t>(h) * a.n_ko * (a.wo_stage_bytes / KS);
+            H1_T(16);
+            // The first min(4, first_wave) phase-A chunks are issued by the four (still idle) warpgroup warps, one each: a TMA issue
+            // costs this thread ~180 cycles, and the first MMA can only start when its chunk has landed.
+#pragma unroll 1
+            for (int kb = 4; kb < first_wave; ++kb) load_a(kb);
+            // K / V^T / early Wo are not needed before the softmax: keep them out of the way of the first phase-A chunks (the
+            // first MMA waits for chunk 0, and everything in flight shares this SM's ~40 B/clk of TMA ingest)
+            mbar_wait_nocall(&bars[B_A_FULL + min(first_wave, 2) - 1], 0);
             const uint8_t* kv_src = a.tiles + (static_cast<size_t>(b) * a.H + h) * a.kv_bytes;
-            auto load_wo = [&](int i) {
-                const int slot = i % a.nw_slots;
-                if (i >= a.nw_slots) mbar_wait_nocall(&bars[B_W_EMPTY + slot], ((i / a.nw_slots) - 1) & 1);
-                const int ks = min(KS, a.n_ko - i * KS);
-                const uint32_t bytes = ks * (a.wo_stage_bytes / KS);
-                mbar_expect_tx(&bars[B_W_FULL + slot], bytes);
-                tma_load_1d(smem + a.wo_off[slot], wo_src + static_cast<size_t>(i) * a.wo_stage_bytes, bytes, &bars[B_W_FULL + slot]);
-            };
-            const int first_wave = min(a.ns_a, a.n_kb);
+            mbar_expect_tx(&bars[B_K_FULL], a.k_tile_bytes);
+            tma_load_1d(sK, kv_src, a.k_tile_bytes, &bars[B_K_FULL]);
+            mbar_expect_tx(&bars[B_V_FULL], a.v_tile_bytes);
+            tma_load_1d(sV, kv_src + a.vx_off, a.v_tile_bytes, &bars[B_V_FULL]);
 #pragma unroll 1
-            for (int kb = 0; kb < a.n_kb; ++kb) {
-                const int slot = kb % a.ns_a;
-                if (kb >= a.ns_a) mbar_wait_nocall(&bars[B_A_EMPTY + slot], ((kb / a.ns_a) - 1) & 1);
-                uint8_t* dst = smem + slot * a.a_stage_bytes;
-                mbar_expect_tx(&bars[B_A_FULL + slot], X_CHUNK_BYTES + a.wq_chunk_bytes);
-                tma_load_3d(dst, &tmX, kb * 64, m0, b, &bars[B_A_FULL + slot]);
-                tma_load_1d(dst + X_CHUNK_BYTES, wq_src + static_cast<size_t>(kb) * a.wq_chunk_bytes, a.wq_chunk_bytes, &bars[B_A_FULL + slot]);
-                if (kb == first_wave - 1) {   // behind the first wave of phase-A chunks: the head's K / V^T tiles and the early Wo stages
-                    mbar_expect_tx(&bars[B_K_FULL], a.k_tile_bytes);
-                    tma_load_1d(sK, kv_src, a.k_tile_bytes, &bars[B_K_FULL]);
-                    mbar_expect_tx(&bars[B_V_FULL], a.v_tile_bytes);
-                    tma_load_1d(sV, kv_src + a.vx_off, a.v_tile_bytes, &bars[B_V_FULL]);
+            for (int i = 0; i < a.wo_early && i < a.n_w; ++i) load_wo(i);
+            H1_T(17);
 #pragma unroll 1
-                    for (int i = 0; i < a.wo_early && i < a.n_w; ++i) load_wo(i);
-                }
-            }
-            if (a.n_w > a.wo_early) {
-                mbar_wait_nocall(&bars[B_PV_ALL], 0);   // the later Wo stages land over the dead P / K / V tiles
-#pragma unroll 1
-                for (int i = a.wo_early; i < a.n_w; ++i) load_wo(i);
+            for (int kb = first_wave; kb < a.n_kb; ++kb) {   // the rest of phase A through the ring
+                mbar_wait_nocall(&bars[B_A_EMPTY + kb % a.ns_a], ((kb / a.ns_a) - 1) & 1);
+                load_a(kb);
             }
         }
         __syncwarp();
-        if (clustered) { cluster_wait(); cluster_arrive(); cluster_wait(); }   // #1, #2: this warp has nothing remote to do
-    } else if (warp == 4) {
-        // ================================================================ MMA issuer (one thread)
+        // #1 wait, #2 arrive BEFORE the late Wo stages: those wait for phase C to free ring slots, and phase C waits for #2
+        if (clustered) { cluster_wait(); if (a.overlay) cluster_arrive(); }
         if (elect_one()) {
+            if (a.n_w > a.wo_early) {
+                mbar_wait_nocall(&bars[B_PV_ALL], 0);   // the later Wo stages land over the dead phase-A / P / K / V regions
+                H1_T(18);
+#pragma unroll 1
+                for (int i = a.wo_early; i < a.n_w; ++i) load_wo(i);
+            }
+            H1_T(19);
+            if (clustered) {
+                // exit handshake, off the MMA thread's path: once every peer's slot has landed here tell each peer so; leave only
+                // when every peer has said the same (then no bulk copy can still be reading this CTA's shared memory)
+                mbar_wait_nocall(&bars[B_OALL], 0);
+                const uint32_t done = smem_u32(&bars[B_DONE]);
+#pragma unroll 1
+                for (int r = 0; r < a.H; ++r)
+                    if (r != h) mbar_arrive_remote(map_to_cta(done, r));
+                mbar_wait_nocall(&bars[B_DONE], 0);
+            }
+        }
+        __syncwarp();
+        if (clustered && a.overlay) cluster_wait();   // #2
+    } else if (warp == 4) {
+        // ================================================================ MMA issuer (one thread); its waits spin (see mbar_wait_spin)
+        if (elect_one()) {
+            H1_T(0);
             if (clustered) mbar_expect_tx(&bars[B_OALL], static_cast<uint32_t>(a.H - 1) * a.slot_bytes);
             // ---- phase A: Q_h = X · Wq_h^T
             const uint32_t idesc_q = umma_idesc_f16(FMT, 128, a.d_pad);
 #pragma unroll 1
             for (int kb = 0; kb < a.n_kb; ++kb) {
                 const int slot = kb % a.ns_a;
-                mbar_wait_nocall(&bars[B_A_FULL + slot], (kb / a.ns_a) & 1);
+                mbar_wait_spin(&bars[B_A_FULL + slot], (kb / a.ns_a) & 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(smem + slot * a.a_stage_bytes);
+                if (kb == 0) H1_T(1);
+                const uint32_t base = smem_u32(smem + a.off_a + slot * a.a_stage_bytes);
                 mma_chain(tmem_base, umma_desc(base, 16, 1024, kLayoutSW128), umma_desc(base + X_CHUNK_BYTES, a.d_pad * 16, 128, kLayoutNone),
                           32, 2 * a.d_pad * 16, 4, idesc_q, static_cast<uint32_t>(kb));
-                umma_commit(&bars[B_A_EMPTY + slot]);
+                if (kb + a.ns_a < a.n_kb) umma_commit(&bars[B_A_EMPTY + slot]);   // only slots that are refilled need the signal
             }
             umma_commit(&bars[B_Q]);
+            H1_T(2);
             // ---- phase B: S = Q_h K^T, then O_t / O_a = P · [V | 1]
-            mbar_wait_nocall(&bars[B_SQ], 0);       // Q_h is in the own slot; the Q accumulator columns are free
-            mbar_wait_nocall(&bars[B_K_FULL], 0);
+            mbar_wait_spin(&bars[B_K_FULL], 0);
+            mbar_wait_spin(&bars[B_SQ], 0);       // Q_h is in the own slot; the Q accumulator columns are free
             tc_fence_after();
+            H1_T(3);
             const uint64_t dQ = umma_desc(smem_u32(sSlot), 2048, 128, kLayoutNone);
             mma_chain(tmem_base, dQ, umma_desc(smem_u32(sK), a.L_pad * 16, 128, kLayoutNone), 2 * 2048, 2 * a.L_pad * 16, a.d_pad / 16,
                       umma_idesc_f16(FMT, 128, a.L_pad), 0);
             umma_commit(&bars[B_S_FULL]);
-            mbar_wait_nocall(&bars[B_P_FULL], 0);
-            mbar_wait_nocall(&bars[B_V_FULL], 0);
+            H1_T(4);
+            mbar_wait_spin(&bars[B_V_FULL], 0);
+            mbar_wait_spin(&bars[B_P_FULL], 0);
             tc_fence_after();
+            H1_T(5);
             {
                 const uint32_t idesc_v = umma_idesc_f16(FMT, 128, a.dv_pad);
                 const uint64_t dP = umma_desc(smem_u32(sP), 2048, 128, kLayoutNone), dV = umma_desc(smem_u32(sV), a.dv_pad * 16, 128, kLayoutNone);
@@ -233,36 +277,33 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
             umma_commit(&bars[B_O_FULL]);
             umma_commit(&bars[B_PV_ALL]);
+            H1_T(6);
         }
         __syncwarp();
-        if (clustered) { cluster_wait(); cluster_arrive(); cluster_wait(); }   // #1; #2 = every CTA's O tile region is free to receive
+        if (clustered) { cluster_wait(); if (a.overlay) { cluster_arrive(); cluster_wait(); } }   // #1; #2 = every CTA's O tile region is free to receive
         if (elect_one()) {
             // ---- phase C: Y[:, own d columns] = O · Wo_h^T over the gathered O tile
-            mbar_wait_nocall(&bars[B_SO], 0);       // own O_h is in its slot, the accumulators have been read
-            if (clustered) mbar_wait_nocall(&bars[B_OALL], 0);   // every peer's slot has landed
+            H1_T(7);
+            mbar_wait_spin(&bars[B_SO], 0);       // own O_h is in its slot, the accumulators have been read
+            H1_T(8);
+            if (clustered) mbar_wait_spin(&bars[B_OALL], 0);   // every peer's slot has landed
             tc_fence_after();
+            H1_T(9);
             const uint32_t idesc_y = umma_idesc_f16(FMT, 128, a.d_pad);
             const uint64_t dO = umma_desc(smem_u32(sO), 2048, 128, kLayoutNone);
 #pragma unroll 1
             for (int i = 0; i < a.n_w; ++i) {
                 const int slot = i % a.nw_slots;
                 const int ks = min(KS, a.n_ko - i * KS);
-                mbar_wait_nocall(&bars[B_W_FULL + slot], (i / a.nw_slots) & 1);
+                mbar_wait_spin(&bars[B_W_FULL + slot], (i / a.nw_slots) & 1);
                 tc_fence_after();
+                if (i == 0) H1_T(10);
                 mma_chain(tmem_base, desc_add(dO, i * KS * 2 * 2048), umma_desc(smem_u32(smem + a.wo_off[slot]), a.d_pad * 16, 128, kLayoutNone),
                           2 * 2048, 2 * a.d_pad * 16, ks, idesc_y, static_cast<uint32_t>(i));
-                umma_commit(&bars[B_W_EMPTY + slot]);
+                if (i + a.nw_slots < a.n_w) umma_commit(&bars[B_W_EMPTY + slot]);
             }
             umma_commit(&bars[B_Y]);
-            if (clustered) {
-                // tell every peer that its slot has landed here; leave only when every peer has said the same (then no bulk copy
-                // can still be reading this CTA's shared memory)
-                const uint32_t done = smem_u32(&bars[B_DONE]);
-#pragma unroll 1
-                for (int r = 0; r < a.H; ++r)
-                    if (r != h) mbar_arrive_remote(map_to_cta(done, r));
-                mbar_wait_nocall(&bars[B_DONE], 0);
-            }
+            H1_T(11);
         }
         __syncwarp();
     } else {
@@ -276,8 +317,13 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int n16q = a.d_pad / 16;             // 2 .. 7
 
         // ---- phase A: Q accumulator -> 16-bit operand tile (own slot)
+        const bool t0 = threadIdx.x == 0;
+        if (warp < first_wave && elect_one()) load_a(warp);   // the first phase-A chunks go out from four warps at once
+        __syncwarp();
+        if (t0) H1_T(24);
         mbar_wait_nocall(&bars[B_Q], 0);
         tc_fence_after();
+        if (t0) H1_T(25);
         {
             uint32_t r[7 * 16];
 #pragma unroll
@@ -291,12 +337,14 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars[B_SQ]);
+        if (t0) H1_T(26);
 
         // ---- phase B: two softmaxes over one score row: text columns [0, Lt), audio columns [Lt_pad, Lt_pad + La); P unnormalised
         const uint32_t tS = tmem_base + lane_taddr;
         float mx_t = -INFINITY, mx_a = -INFINITY;
         mbar_wait_nocall(&bars[B_S_FULL], 0);
         tc_fence_after();
+        if (t0) H1_T(27);
         if (N16 > 0) {
             uint32_t s[(N16 > 0 ? N16 : 1) * 16];
 #pragma unroll
@@ -311,6 +359,7 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 if (c < LT16) mx_t = fmaxf(mx_t, max16(s + c * 16)); else mx_a = fmaxf(mx_a, max16(s + c * 16));
             }
             const float mxs_t = mx_t * sl, mxs_a = mx_a * sl;
+            if (t0) H1_T(28);
 #pragma unroll
             for (int c = 0; c < N16; ++c) exp_store16<FMT>(s + c * 16, sl, c < LT16 ? mxs_t : mxs_a, sP_row + c * 2 * 2048);
         } else {
@@ -338,6 +387,7 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars[B_P_FULL]);
+        if (t0) H1_T(29);
 
         // ---- O_h = O_t / l_t + ap_scale * O_a / l_a -> 16 bit, over Q_h in the own slot; l_t, l_a = accumulator column d_pad
         //      (ones row of the extended V^T tile).  A segment that does not exist reads the other accumulator with weight 0.
@@ -346,6 +396,7 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const uint32_t tOt = a.Lt > 0 ? tO : tO + a.dv_pad, tOa = a.La > 0 ? tO + a.dv_pad : tO;
             mbar_wait_nocall(&bars[B_O_FULL], 0);
             tc_fence_after();
+            if (t0) H1_T(30);
             uint32_t lt, la;
             tmem_ld1(tOt + a.d_pad, lt);
             tmem_ld1(tOa + a.d_pad, la);
@@ -379,24 +430,33 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bars[B_SO]);
+        if (t0) H1_T(31);
         if (clustered) {
-            // all-gather of the O slots over distributed shared memory: once every CTA of the cluster has finished with the shared
-            // memory its O tile region overlays (#2), push the own slot into the same slot of every peer
-            cluster_wait();      // #1
-            cluster_arrive();    // #2 (release: orders the st.shared of the slot before the peers' / the pusher's view of it)
-            cluster_wait();
-            if (threadIdx.x == 0) {
+            // all-gather of the O slots over distributed shared memory: push the own slot into the same slot of every peer.  Overlay
+            // plan: only once every CTA of the cluster has finished with the shared memory its O tile region overlays (#2).
+            cluster_wait();      // #1: the peers' barriers exist
+            if (a.overlay) {
+                cluster_arrive();    // #2 (release: orders the st.shared of the slot before the pusher's view of it)
+                cluster_wait();
+            } else {
+                named_bar_sync(1, 128);   // every row of the slot is written (and fenced to the async proxy)
+            }
+            if (t0) H1_T(32);
+            if (elect_one()) {   // warp w pushes to ranks w and w + 4: the copies are issued from four warps at once
                 const uint32_t slot = smem_u32(sSlot), bar = smem_u32(&bars[B_OALL]);
 #pragma unroll 1
-                for (int r = 0; r < a.H; ++r)
+                for (int r = warp; r < a.H; r += 4)
                     if (r != h) dsmem_bulk_copy(map_to_cta(slot, r), sSlot, a.slot_bytes, map_to_cta(bar, r));
             }
+            __syncwarp();
+            if (t0) H1_T(33);
         }
 
         // ---- phase C epilogue: Y accumulator (+ bias) -> 16 bit -> core-matrix staging tile -> one 4-D tensor-TMA store.
         //      The staging tile is the slot of the NEXT rank: received, consumed by the MMAs (B_Y), and never the source of a push.
         mbar_wait_nocall(&bars[B_Y], 0);
         tc_fence_after();
+        if (t0) H1_T(34);
         {
             uint8_t* sStage = sO + ((h + 1) % a.H) * a.slot_bytes;
             const uint32_t stage_row = smem_u32(sStage) + row * 16;
@@ -421,7 +481,9 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 if (a.accumulate) tma_reduce_add_4d(&tmY, sStage, 0, m0, h * (a.d / 8), b);
                 else tma_store_4d(&tmY, sStage, 0, m0, h * (a.d / 8), b);
                 tma_store_commit();
+                H1_T(35);
                 tma_store_wait_read();
+                H1_T(36);
             }
         }
     }
@@ -433,8 +495,8 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
 struct H1Plan {
     bool ok;
-    int ns_a, n_w, nw_slots, wo_early, p_in_r0;
-    uint32_t off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, wo_stage_bytes, smem_bytes, wo_off[MAX_W];
+    int ns_a, n_w, nw_slots, wo_early, p_in_r0, overlay;
+    uint32_t off_a, off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, wo_stage_bytes, smem_bytes, wo_off[MAX_W];
 };
 
 H1Plan h1_plan(const H1Geom& g, int Lt, int La) {
@@ -446,38 +508,51 @@ H1Plan h1_plan(const H1Geom& g, int Lt, int La) {
     if (kg.L_pad + 2 * kg.dv_pad > 512) return p;           // tensor-memory columns of phase B
     const uint32_t slot = static_cast<uint32_t>(g.d_pad) * 256, r0 = static_cast<uint32_t>(g.Nq) * 256;
     p.p_bytes = 128u * kg.L_pad * 2;
-    p.a_stage_bytes = X_CHUNK_BYTES + static_cast<uint32_t>(g.d_pad) * 128;
+    p.a_stage_bytes = static_cast<uint32_t>(align_up(X_CHUNK_BYTES + static_cast<size_t>(g.d_pad) * 128, 1024));   // SWIZZLE_128B boxes: 1024-aligned
     p.wo_stage_bytes = KS * static_cast<uint32_t>(g.d_pad) * 32;
     p.n_w = (g.Nq / 16 + KS - 1) / KS;
     const uint32_t limit = 227u * 1024u - 1024u;            // minus the alignment slack of the dynamic shared-memory base
     const uint32_t tail = BAR_REGION_BYTES + static_cast<uint32_t>(g.d_pad) * 4;
-    for (int in_r0 = 1; in_r0 >= 0; --in_r0) {
-        if (in_r0 && !(g.H >= 2 && static_cast<uint32_t>(g.H / 2) * slot >= p.p_bytes)) continue;
-        uint32_t off = r0;
-        p.p_in_r0 = in_r0;
-        p.off_p = off;
-        if (!in_r0) off += static_cast<uint32_t>(align_up(p.p_bytes, 1024));
-        const uint32_t a_limit = off;                        // the phase-A ring may use [0, a_limit)
-        p.off_k = off; off += static_cast<uint32_t>(align_up(kg.k_tile_bytes, 128));
-        p.off_v = off; off += static_cast<uint32_t>(align_up(kg.vx_tile_bytes, 1024));
-        const uint32_t ovl_begin = in_r0 ? p.off_k : p.off_p, ovl_end = off;
-        p.ns_a = static_cast<int>(std::min<uint32_t>(std::min<uint32_t>(MAX_A, g.n_kb), a_limit / p.a_stage_bytes));
-        if (p.ns_a < std::min(2, g.n_kb)) continue;
-        if (off + tail > limit) continue;
-        // Wo ring: stages with a region of their own (loadable from the start) + stages over the dead P / K / V tiles
+    const uint32_t kv = static_cast<uint32_t>(align_up(kg.k_tile_bytes, 128) + align_up(kg.vx_tile_bytes, 1024));
+    // Wo ring over [ovl_begin, ovl_end) (dead after the last P·V) + up to two stages of their own behind `off`
+    auto finish = [&](uint32_t off, uint32_t ovl_begin, uint32_t ovl_end) -> bool {
+        if (off + tail > limit) return false;
         int early = static_cast<int>(std::min<uint32_t>((limit - tail - off) / p.wo_stage_bytes, 2));
         early = std::min(early, p.n_w);
         int late = static_cast<int>((ovl_end - ovl_begin) / p.wo_stage_bytes);
         late = std::min(late, MAX_W - early);
         late = std::min(late, p.n_w - early);
-        if (early + late < std::min(2, p.n_w)) continue;
+        if (early + late < std::min(2, p.n_w)) return false;
         p.wo_early = early; p.nw_slots = early + late;
         for (int i = 0; i < early; ++i) { p.wo_off[i] = off; off += p.wo_stage_bytes; }
         for (int i = 0; i < late; ++i) p.wo_off[early + i] = ovl_begin + i * p.wo_stage_bytes;
         p.off_bar = static_cast<uint32_t>(align_up(off, 128));
         p.smem_bytes = p.off_bar + tail + 1024;
-        p.ok = p.off_bar + tail <= limit;
-        if (p.ok) return p;
+        return p.off_bar + tail <= limit;
+    };
+    // plan 1 (no overlay): [O tile][phase-A ring | P tile][K][V][early Wo]: nothing but its owner and the peers' pushes ever writes the
+    // O tile, so a slot is pushed the moment it exists
+    for (int ns = std::min(4, g.n_kb); ns >= std::min(2, g.n_kb); --ns) {
+        p.overlay = 0; p.p_in_r0 = 0; p.ns_a = ns;
+        p.off_a = r0; p.off_p = r0;
+        uint32_t off = r0 + static_cast<uint32_t>(align_up(std::max<uint32_t>(ns * p.a_stage_bytes, p.p_bytes), 1024));
+        p.off_k = off; p.off_v = off + static_cast<uint32_t>(align_up(kg.k_tile_bytes, 128));
+        off += kv;
+        if (finish(off, r0, off)) { p.ok = true; return p; }
+    }
+    // plan 2 (overlay): the phase-A ring lies over the O tile, and so does the P tile when the larger half next to the own slot holds it
+    for (int in_r0 = 1; in_r0 >= 0; --in_r0) {
+        if (in_r0 && !(g.H >= 2 && static_cast<uint32_t>(g.H / 2) * slot >= p.p_bytes)) continue;
+        p.overlay = 1; p.p_in_r0 = in_r0;
+        uint32_t off = r0;
+        p.off_a = 0; p.off_p = off;
+        if (!in_r0) off += static_cast<uint32_t>(align_up(p.p_bytes, 1024));
+        const uint32_t a_limit = off;                        // the phase-A ring may use [0, a_limit)
+        p.off_k = off; p.off_v = off + static_cast<uint32_t>(align_up(kg.k_tile_bytes, 128));
+        off += kv;
+        p.ns_a = static_cast<int>(std::min<uint32_t>(std::min<uint32_t>(MAX_A, g.n_kb), a_limit / p.a_stage_bytes));
+        if (p.ns_a < std::min(2, g.n_kb)) continue;
+        if (finish(off, in_r0 ? p.off_k : p.off_p, off)) { p.ok = true; return p; }
     }
     p.ok = false;
     return p;
@@ -548,10 +623,18 @@ int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, co
     a.p_bytes = p.p_bytes;
     a.slot_bytes = static_cast<uint32_t>(g.d_pad) * 256;
     a.ns_a = p.ns_a; a.n_w = p.n_w; a.nw_slots = p.nw_slots; a.wo_early = p.wo_early; a.n_ko = g.Nq / 16;
-    a.p_in_r0 = p.p_in_r0;
-    a.off_p = p.off_p; a.off_k = p.off_k; a.off_v = p.off_v; a.off_bar = p.off_bar;
+    a.p_in_r0 = p.p_in_r0; a.overlay = p.overlay;
+    a.off_a = p.off_a; a.off_p = p.off_p; a.off_k = p.off_k; a.off_v = p.off_v; a.off_bar = p.off_bar;
     for (int i = 0; i < MAX_W; ++i) a.wo_off[i] = p.wo_off[i];
     a.accumulate = accumulate ? 1 : 0;
+    // diagnostic timeline (APX_SITE_TRACE=1): synchronises and prints, never enabled on the product path
+    static const bool trace_on = [] { const char* e = getenv("APX_SITE_TRACE"); return e && e[0] == '1'; }();
+    static long long* trace_buf = nullptr;
+    if (trace_on) {
+        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 64 * sizeof(long long)));
+        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 64 * sizeof(long long), st));
+        a.trace = trace_buf;
+    }
 
     // kernel variant: score rows of 32 / 48 / 144 columns (La = 8 / 32 / 128 behind 1..16 text tokens) stay in registers
     const int n16 = kg.L_pad / 16;
@@ -582,6 +665,24 @@ int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, co
     cfg.numAttrs = H > 1 ? 1 : 0;
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmY, a));
     APX_LAUNCH_CHECK("ipattn_site_h1_kernel");
+    if (trace_on) {
+        static int printed = 0;
+        long long t[64];
+        APX_CUDA(cudaStreamSynchronize(st));
+        APX_CUDA(cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost));
+        if (printed++ < 3) {
+            long long t0 = t[0];
+            for (int i = 0; i < 64; ++i) if (t[i] && t[i] < t0) t0 = t[i];
+            auto rel = [&](int slot) { return t[slot] ? t[slot] - t0 : -1; };
+            printf("[apx h1 trace] Bc=%d S=%d C=%d H=%d Lt=%d La=%d ns_a=%d nw_slots=%d/%d early=%d p_in_r0=%d overlay=%d smem=%u (cycles since the first stamp; CTA 0)\n", Bc, S, C, H,
+                   Lt, La, p.ns_a, p.nw_slots, p.n_w, p.wo_early, p.p_in_r0, p.overlay, p.smem_bytes);
+            printf("  mma : start %lld a_full0 %lld q_committed %lld sq+k_seen %lld s_issued %lld p+v_seen %lld pv_issued %lld | cluster2 %lld so_seen %lld oall_seen %lld wo_full0 %lld y_committed %lld\n",
+                   rel(0), rel(1), rel(2), rel(3), rel(4), rel(5), rel(6), rel(7), rel(8), rel(9), rel(10), rel(11));
+            printf("  tma : start %lld first_loads_issued %lld pv_all_seen %lld done %lld\n", rel(16), rel(17), rel(18), rel(19));
+            printf("  wg  : top %lld q_seen %lld sq_arrived %lld s_seen %lld max_done %lld p_arrived %lld o_full_seen %lld so_arrived %lld cluster2 %lld pushed %lld | y_seen %lld store_issued %lld store_read %lld\n",
+                   rel(24), rel(25), rel(26), rel(27), rel(28), rel(29), rel(30), rel(31), rel(32), rel(33), rel(34), rel(35), rel(36));
+        }
+    }
     return APX_OK;
 }
 

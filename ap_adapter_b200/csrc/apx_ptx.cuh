@@ -88,6 +88,15 @@ __device__ __forceinline__ void mbar_wait_nocall(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Spinning wait for the ONE thread whose wake-up latency is the critical path (the MMA issuer): a suspended waiter wakes some
+// 250-300 cycles after the barrier completes (profiles/r2c_h1_trace.txt), a spinning one within a few tens.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) asm volatile("trap;");
+    }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

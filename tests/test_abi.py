@@ -42,15 +42,29 @@ def test_no_compute_queries_work_without_gpu():
     assert lib.apx_ctx_kv_bytes(2, 8, 128, 250, 8) == 0  # C not divisible by H
     assert lib.apx_ipattn_workspace_bytes(2, 1000, 256) >= 2 * 2 * 1000 * 256 * 2
     assert lib.apx_audiomae_workspace_bytes(1) > 513 * 3072 * 2
-    # site-kernel coverage and packed-weight size: Wq as [C/64][8][H*d_pad][8] + Wo as [H*d_pad/8][C][8] 16-bit elements
-    # ... one (Wq, Wo) pair per supported cluster size (1, 2, 4 CTAs per query tile; C / cs must be a multiple of 64)
-    assert lib.apx_ipattn_pack_bytes(256, 8) == 3 * 2 * 256 * 256 * 2
-    assert lib.apx_ipattn_pack_bytes(128, 8) == 2 * 2 * 128 * 128 * 2
-    assert lib.apx_ipattn_pack_bytes(320, 8) == 0 and lib.apx_ipattn_pack_bytes(384, 8) == 0   # C > 256: three-kernel path
-    assert lib.apx_ipattn_pack_bytes(640, 8) == 0
+    # packed-weight size: the all-heads kernel's sections (Wq as [C/64][8][H*d_pad][8] + Wo as [H*d_pad/8][C][8], one pair per
+    # supported cluster size 1 / 2 / 4; C <= 256 only) + the one-head kernel's sections (Wq [H][C/64][8][d_pad][8] + Wo [H][Nq/8][d_pad][8])
+    assert lib.apx_ipattn_pack_bytes(256, 8) == 3 * 2 * 256 * 256 * 2 + 2 * 256 * 256 * 2
+    assert lib.apx_ipattn_pack_bytes(128, 8) == 2 * 2 * 128 * 128 * 2 + 2 * 128 * 128 * 2
+    assert lib.apx_ipattn_pack_bytes(384, 8) == 384 * 384 * 2 * 2 and lib.apx_ipattn_pack_bytes(640, 8) == 640 * 640 * 2 * 2
+    assert lib.apx_ipattn_pack_bytes(320, 8) == 384 * 320 * 2 + 384 * 384 * 2         # d = 40 -> d_pad = 48: Nq = 384
+    assert lib.apx_ipattn_pack_bytes(512, 16) == 0                                    # 16 heads: neither fused kernel
+    # coverage: contexts of up to 256 padded tokens fuse at every AudioLDM2 width; the un-pooled 8 + 512 context takes three kernels
     assert lib.apx_ipattn_fused_ok(256, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(256, 8, 8, 8) == 1
-    assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(384, 8, 8, 128) == 0
-    assert lib.apx_ipattn_fused_ok(640, 8, 8, 8) == 0
+    assert lib.apx_ipattn_fused_ok(384, 8, 8, 128) == 1 and lib.apx_ipattn_fused_ok(640, 8, 8, 128) == 1
+    assert lib.apx_ipattn_fused_ok(320, 8, 77, 8) == 1
+    assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(512, 16, 8, 32) == 0
+    # kernel choice (measured policy, apx_api.cu::pick_site_kernel): all-heads wherever it applies, one-head for small grids at
+    # C = 320 / 384, three kernels at C = 640 and for large grids
+    assert lib.apx_ipattn_site_kernel(2, 1000, 256, 8, 8, 128) == 1 and lib.apx_ipattn_site_kernel(16, 1000, 256, 8, 8, 128) == 1
+    assert lib.apx_ipattn_site_kernel(2, 252, 384, 8, 8, 128) == 2 and lib.apx_ipattn_site_kernel(16, 252, 384, 8, 8, 128) == 0
+    assert lib.apx_ipattn_site_kernel(2, 64, 640, 8, 8, 128) == 0
+    assert lib.apx_set_site_variant(_lib.APX_SITE_ONEHEAD) == 0
+    try:
+        assert lib.apx_ipattn_site_kernel(2, 64, 640, 8, 8, 128) == 2 and lib.apx_ipattn_site_kernel(2, 1000, 256, 8, 8, 128) == 2
+    finally:
+        assert lib.apx_set_site_variant(_lib.APX_SITE_AUTO) == 0
+    assert lib.apx_set_site_variant(9) == 1
 
 
 def test_null_pointers_are_rejected_not_dereferenced():

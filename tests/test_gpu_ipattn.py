@@ -85,6 +85,29 @@ def test_site_edge_shapes(shape):
     assert rel_err(y, oracle_site(case, torch.float16)) < TOL[torch.float16]
 
 
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
+@pytest.mark.parametrize("name", ["cfg1", "site256_real", "site384", "site640", "ctx2d", "text_only"])
+def test_one_head_site_kernel_matches_oracle(name, dtype):
+    """The one-head-per-CTA (cluster) site kernel pinned on every shape it covers — C = 320 (d = 40, padded to 48) / 256 / 384 / 640,
+    with and without audio tokens — at the same bar as the product's own choice of kernel."""
+    lib = _lib.load()
+    case = cases.make_ipattn_case(name)
+    bc, s, c = (case["x"].shape if case["x"].dim() == 3 else (1,) + tuple(case["x"].shape))
+    lctx = case["ctx"].shape[-2]
+    lt = min(case["num_tokens"], lctx)
+    assert lib.apx_set_site_variant(_lib.APX_SITE_ONEHEAD) == 0
+    try:
+        assert lib.apx_ipattn_site_kernel(bc, s, c, case["heads"], lt, lctx - lt) == 2
+        n0 = _lib.launch_count()
+        y = run_site(case, dtype)
+        # ctx K/V build (4 GEMMs + merge + pack) + weight packs + ONE site launch: the site itself must not be three kernels
+        assert _lib.launch_count() - n0 <= 4 + 2 + 2 + 1
+        ok, errs = site_within_bar(y, case, dtype, "site_onehead/" + name)
+    finally:
+        assert lib.apx_set_site_variant(_lib.APX_SITE_AUTO) == 0
+    assert ok, errs
+
+
 def test_tensor_core_and_cuda_core_paths_agree():
     lib = _lib.load()
     case = random_site_case(2, 300, 384, 8, 8, 128, seed=5)

@@ -13,6 +13,13 @@ from gpu_util import rel_err
 pytestmark = pytest.mark.gpu
 
 
+def _site_launches(bc=2, la=128) -> int:
+    """libapx launches of the 32 adapter sites of one UNet forward at the 10 s latent: one per site where a fused kernel is picked
+    (apx_ipattn_site_kernel != 0), three otherwise (SURVEY.md appendix B geometry: 10 x (1000, 256), 10 x (252, 384), 12 x (64, 640))."""
+    lib = _lib.load()
+    return sum(n * (1 if lib.apx_ipattn_site_kernel(bc, s, c, 8, 8, la) else 3) for n, s, c in ((10, 1000, 256), (10, 252, 384), (12, 64, 640)))
+
+
 def _fused_ff_count(unet) -> int:
     with torch.no_grad():
         return sum(m.fused_ok(torch.empty(1, m.net[2].out_features, device="cuda", dtype=torch.float16))
@@ -54,12 +61,12 @@ def test_unet_step_matches_pytorch_processors(setup):
         n0 = _lib.launch_count()
         y = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
         launched = _lib.launch_count() - n0
-    # every adapter site went through libapx: the 10 C = 256 sites run the single site kernel, the 22 C = 384 / 640 sites
-    # the three-kernel tcgen05 path; context caches / packed weights are built on first use
+    # every adapter site went through libapx: the C = 256 sites run the all-heads site kernel, the C = 384 sites the one-head
+    # (cluster) site kernel, the C = 640 sites the three-kernel tcgen05 path; context caches / packed weights are built on first use
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values())
     assert n_ff == 128 and n_plain == 224
-    assert launched >= 10 + 22 * 3 + 2 * n_ff, launched
+    assert launched >= _site_launches() + 2 * n_ff, launched
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
     assert rel_err(y, y_ref) < 1e-2
@@ -81,7 +88,7 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     # residual GEMM is opt-in, APX_FOLD_RESIDUAL=1)
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values()) if BasicTransformerBlock.fold_residual is True else 0
-    assert per_step == 10 * 1 + 22 * 3 + 2 * n_ff + n_plain
+    assert per_step == _site_launches() + 2 * n_ff + n_plain
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)
