@@ -57,6 +57,8 @@ SYMBOLS = {
     "apx_ipattn_fwd_add": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_ipattn_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "apx_ipattn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "apx_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "apx_add_bias_nhwc": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "apx_audiomae_workspace_bytes": (_Z, [_I]),
     "apx_audiomae_fwd": (_I, [_P, POINTER(VitWeights), _P, _I, _I, _I, _P, _Z, _P]),
     "apx_audiomae_encode": (_I, [_P, POINTER(VitWeights), _P, _I, _P, _Z, _P]),
@@ -217,6 +219,45 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, l0:
                                 v.stride(1), ptr(o), o.stride(0), o.stride(1), b, s, heads, c // heads, l, l0, w0, w1,
                                 dtype_code(q.dtype), stream_ptr()), "apx_attention")
     return o
+
+
+def groupnorm_nhwc_ok(hw: int, c: int, groups: int) -> bool:
+    """Shapes apx_groupnorm_nhwc takes (one group's HW x C/groups values are staged in shared memory as fp32)."""
+    return c % groups == 0 and (c // groups) % 4 == 0 and hw * (c // groups) * 4 <= 200 * 1024
+
+
+def groupnorm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+                   chan_bias: torch.Tensor | None = None, bc_add: torch.Tensor | None = None) -> torch.Tensor:
+    """[SiLU] GroupNorm(x + chan_bias[c] + bc_add[b, c]) on a channels-last (B, C, H, W) 16-bit tensor (apx_groupnorm_nhwc).
+    gamma / beta / chan_bias fp32 (C,), bc_add (B, C) in x's dtype.  Returns a channels-last tensor of x's shape."""
+    lib = load()
+    dev = require_cuda(x, gamma, beta, chan_bias, bc_add)
+    b, c, h, w = x.shape
+    assert x.is_contiguous(memory_format=torch.channels_last) and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    if bc_add is not None:
+        assert bc_add.shape == (b, c) and bc_add.dtype == x.dtype and bc_add.stride(1) == 1
+    if chan_bias is not None:
+        assert chan_bias.dtype == torch.float32 and chan_bias.numel() == c
+    with torch.cuda.device(dev):
+        check(lib.apx_groupnorm_nhwc(ptr(x), ptr(gamma), ptr(beta), ptr(chan_bias), ptr(bc_add), bc_add.stride(0) if bc_add is not None else 0,
+                                     ptr(y), b, h * w, c, groups, float(eps),
+                                     1 if silu else 0, dtype_code(x.dtype), stream_ptr()), "apx_groupnorm_nhwc")
+    return y
+
+
+def add_bias_nhwc(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None, scale: float = 1.0) -> torch.Tensor:
+    """(a + b + bias[c]) * scale on channels-last (B, C, H, W) 16-bit tensors (apx_add_bias_nhwc)."""
+    lib = load()
+    dev = require_cuda(a, b, bias)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    assert a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)
+    n, c, h, w = a.shape
+    y = torch.empty_like(a, memory_format=torch.channels_last)
+    with torch.cuda.device(dev):
+        check(lib.apx_add_bias_nhwc(ptr(a), ptr(b), ptr(bias), ptr(y), n * h * w, c, float(scale), dtype_code(a.dtype), stream_ptr()),
+              "apx_add_bias_nhwc")
+    return y
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:

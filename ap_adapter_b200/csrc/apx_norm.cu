@@ -1,0 +1,174 @@
+// apx_norm.cu — the normalisation / elementwise neighbours of the adapter sites inside the AudioLDM2 UNet blocks (SURVEY.md §8f-2:
+// pipeline/modeling_audioldm2.py:1140-1156, 1317-1333, 1492-1508 call ResnetBlock2D / Transformer2DModel around every attn2 site).
+// HBM-bound CUDA-core kernels on channels-last (NHWC) 16-bit activations:
+//
+//   groupnorm_nhwc   y = [SiLU] GroupNorm(x + chan_bias[c] + bc_add[b, c])   one kernel for what the stock graph runs as conv-bias add,
+//                    time-embedding add, three GroupNorm kernels and SiLU; reads and writes NHWC, so the cuDNN convolutions
+//                    around it take their native layout and the token view [B, H*W, C] of a Transformer2DModel is free.
+//   add_bias_nhwc    y = (a + b + bias[c]) * scale                           the ResnetBlock2D output: shortcut + conv2 + conv biases.
+#include "apx_internal.h"
+#include "apx_ptx.cuh"
+#include <algorithm>
+
+namespace apx {
+namespace {
+
+struct GnArgs {
+    const uint16_t* x;        // [B, HW, C] (NHWC)
+    uint16_t* y;              // [B, HW, C]
+    const float* gamma;       // [C]
+    const float* beta;        // [C]
+    const float* chan_bias;   // [C] or null: added to x before the statistics (the bias of the convolution that produced x)
+    const uint16_t* bc_add;   // [B, C] 16-bit (row stride bc_stride elements) or null: added to x before the statistics (time-embedding projection)
+    int64_t bc_stride;
+    int B, HW, C, G, cpg;
+    float eps;
+    int silu, fmt;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {   // blockDim.x <= 1024, every thread gets the total
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();                      // red may still be read from the previous call
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = lane < nw ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+// One CTA per (group, batch element).  The group's HW x cpg values are staged ONCE in shared memory as fp32 (with the two adds
+// applied), so global memory is read once and written once; mean and variance are two exact passes over shared memory.
+__global__ void __launch_bounds__(512) groupnorm_nhwc_kernel(GnArgs a) {
+    extern __shared__ float sv[];           // [HW][cpg]
+    __shared__ float red[32];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int q4 = a.cpg / 4;               // 4-channel (8-byte) pieces per pixel of this group
+    const int n4 = a.HW * q4;
+    const uint16_t* xg = a.x + static_cast<size_t>(b) * a.HW * a.C + g * a.cpg;
+    uint16_t* yg = a.y + static_cast<size_t>(b) * a.HW * a.C + g * a.cpg;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const int p = i / q4, q = i - p * q4;
+        const uint2 raw = *reinterpret_cast<const uint2*>(xg + static_cast<size_t>(p) * a.C + q * 4);
+        float v[4];
+        unpack16(raw.x, a.fmt, v[0], v[1]);
+        unpack16(raw.y, a.fmt, v[2], v[3]);
+        const int c = g * a.cpg + q * 4;
+        if (a.chan_bias) {
+            const float4 cb = *reinterpret_cast<const float4*>(a.chan_bias + c);
+            v[0] += cb.x; v[1] += cb.y; v[2] += cb.z; v[3] += cb.w;
+        }
+        if (a.bc_add) {
+            const uint2 t = *reinterpret_cast<const uint2*>(a.bc_add + static_cast<size_t>(b) * a.bc_stride + c);
+            float t0, t1, t2, t3;
+            unpack16(t.x, a.fmt, t0, t1);
+            unpack16(t.y, a.fmt, t2, t3);
+            v[0] += t0; v[1] += t1; v[2] += t2; v[3] += t3;
+        }
+        *reinterpret_cast<float4*>(sv + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        sum += (v[0] + v[1]) + (v[2] + v[3]);
+    }
+    const float n = static_cast<float>(a.HW) * a.cpg;
+    const float mean = block_sum(sum, red) / n;
+    float sq = 0.f;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(block_sum(sq, red) / n + a.eps);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const int p = i / q4, q = i - p * q4;
+        const int c = g * a.cpg + q * 4;
+        const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
+        const float4 ga = *reinterpret_cast<const float4*>(a.gamma + c), be = *reinterpret_cast<const float4*>(a.beta + c);
+        float o[4] = {(v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y, (v.z - mean) * rstd * ga.z + be.z,
+                      (v.w - mean) * rstd * ga.w + be.w};
+        if (a.silu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + __expf(-o[k]));
+        }
+        uint2 out;
+        out.x = pack16(o[0], o[1], a.fmt);
+        out.y = pack16(o[2], o[3], a.fmt);
+        *reinterpret_cast<uint2*>(yg + static_cast<size_t>(p) * a.C + q * 4) = out;
+    }
+}
+
+// y = (a + b + bias[c]) * scale over [rows, C] 16-bit, 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const uint4* __restrict__ A, const uint4* __restrict__ Bm, const float* __restrict__ bias,
+                                                           uint4* __restrict__ Y, size_t n8, int C8, float scale, int fmt) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4 a = A[i], b = Bm[i];
+        const int c = static_cast<int>(i % C8) * 8;
+        float bs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+        }
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a0, a1, b0, b1;
+            unpack16(aw[k], fmt, a0, a1);
+            unpack16(bw[k], fmt, b0, b1);
+            ow[k] = pack16((a0 + b0 + bs[2 * k]) * scale, (a1 + b1 + bs[2 * k + 1]) * scale, fmt);
+        }
+        Y[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+}  // namespace
+}  // namespace apx
+
+using namespace apx;
+
+extern "C" {
+
+int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, const float* chan_bias, const void* bc_add, int64_t bc_stride,
+                       void* y, int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream) {
+    APX_REQUIRE(x && gamma && beta && y, APX_EINVAL, "apx_groupnorm_nhwc: null pointer");
+    APX_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, APX_EINVAL, "apx_groupnorm_nhwc: bad shape B=%d HW=%d C=%d G=%d", B, HW, C,
+                groups);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: dtype %d", dtype);
+    const int cpg = C / groups;
+    APX_REQUIRE(cpg % 4 == 0, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: %d channels per group (need a multiple of 4)", cpg);
+    const size_t smem = static_cast<size_t>(HW) * cpg * 4;
+    APX_REQUIRE(smem <= 200 * 1024, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: a group of %d x %d values needs %zu B of shared memory", HW, cpg, smem);
+    APX_REQUIRE(B <= 65535, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: B=%d", B);
+    APX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(beta) & 15) == 0 && (reinterpret_cast<uintptr_t>(chan_bias) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bc_add) & 7) == 0 && (bc_add == nullptr || (bc_stride >= C && bc_stride % 4 == 0)),
+                APX_EINVAL, "apx_groupnorm_nhwc: misaligned pointer / bad bc_add stride");
+    static std::atomic<uint64_t> attr_mask{0};
+    if (first_use_on_device(attr_mask))
+        APX_CUDA(cudaFuncSetAttribute(groupnorm_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GnArgs a{static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), gamma, beta, chan_bias, static_cast<const uint16_t*>(bc_add), bc_stride,
+             B, HW, C, groups, cpg, eps, silu ? 1 : 0, dtype == APX_F16 ? 0 : 1};
+    const int n4 = HW * (cpg / 4);
+    const int threads = n4 >= 2048 ? 512 : n4 >= 512 ? 256 : 128;
+    groupnorm_nhwc_kernel<<<dim3(groups, B), threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    APX_LAUNCH_CHECK("groupnorm_nhwc_kernel");
+    return APX_OK;
+}
+
+int apx_add_bias_nhwc(const void* a, const void* b, const float* bias, void* y, int64_t rows, int C, float scale, int dtype, void* stream) {
+    APX_REQUIRE(a && b && y, APX_EINVAL, "apx_add_bias_nhwc: null pointer");
+    APX_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, APX_EINVAL, "apx_add_bias_nhwc: bad shape rows=%lld C=%d (C %% 8 == 0)", static_cast<long long>(rows), C);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_add_bias_nhwc: dtype %d", dtype);
+    APX_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                APX_EINVAL, "apx_add_bias_nhwc: misaligned pointer");
+    const size_t n8 = static_cast<size_t>(rows) * C / 8;
+    const int blocks = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 8));
+    add_bias_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b), bias,
+                                                                               static_cast<uint4*>(y), n8, C / 8, scale, dtype == APX_F16 ? 0 : 1);
+    APX_LAUNCH_CHECK("add_bias_nhwc_kernel");
+    return APX_OK;
+}
+
+}  // extern "C"

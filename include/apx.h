@@ -22,6 +22,9 @@
  *                         (attention_processor.py:274,429,443; timm Attention in models_mae.py:566)
  *   apx_audiomae_fwd      audio_encoder/AudioMAE.py:190-212 (forward) -> :37-55 ->
  *                         audio_encoder/models_mae.py:548-570 (encoder) -> AudioMAE.py:148-182 (pool)
+ *   apx_groupnorm_nhwc    nn.GroupNorm + F.silu (+ the conv-bias / time-embedding adds in front of it) inside diffusers' ResnetBlock2D /
+ *   apx_add_bias_nhwc     Transformer2DModel as wired by pipeline/modeling_audioldm2.py:1047-1058,1223-1233,1399-1410 (third-party
+ *                         leaves)
  *   apx_fbank             audio_encoder/AudioMAE.py:356-394 (extract_kaldi_fbank_feature; torchaudio's Kaldi fbank is a
  *                         third-party dependency of the reference, restated from torchaudio 2.x compliance/kaldi.py)
  *   apx_patch_embed       audio_encoder/models_mae.py:19-44 (PatchEmbed_org) + :552,561-563
@@ -166,6 +169,21 @@ size_t apx_ipattn_bwd_workspace_bytes(int Bc, int S, int C, int La);
 int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo, const void* cache, const void* ctx, void* dX,
                    float* dWk_ip, float* dWv_ip, int Bc, int S, int C, int H, int Lt, int La, int Dctx, float ap_scale, int dtype,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- UNet block neighbours of the adapter sites (pipeline/modeling_audioldm2.py:1140-1156, 1317-1333, 1492-1508:
+ *      ResnetBlock2D / Transformer2DModel around every attn2 call site), on channels-last 16-bit activations ------------------- */
+/*
+ * y = [SiLU]( GroupNorm_groups( x + chan_bias[c] + bc_add[b, c] ) * gamma[c] + beta[c] )
+ *   x, y [B, HW, C] `dtype` (NHWC); gamma, beta fp32[C]; chan_bias fp32[C] or NULL (the bias of the convolution that produced x);
+ *   bc_add [B, C] `dtype`, rows bc_stride elements apart, or NULL (ResnetBlock2D's time-embedding projection).  Statistics in fp32 over the SUMMED value, two
+ *   exact passes; one rounding at the end.  Replaces conv-bias add + temb add + nn.GroupNorm (3 ATen kernels) + F.silu.
+ *   Requires (C / groups) % 4 == 0 and HW * (C / groups) * 4 <= 200 KB (one group is staged in shared memory).
+ */
+int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, const float* chan_bias, const void* bc_add, int64_t bc_stride,
+                       void* y, int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
+/* y = (a + b + bias[c]) * scale over [rows, C] `dtype` (C % 8 == 0); bias fp32[C] or NULL.  ResnetBlock2D's output:
+ * (shortcut(x) + conv2(h) + conv biases) / output_scale_factor. */
+int apx_add_bias_nhwc(const void* a, const void* b, const float* bias, void* y, int64_t rows, int C, float scale, int dtype, void* stream);
 
 /* ---- AudioMAE encoder ---------------------------------------------------------------- */
 typedef struct apx_vit_block {

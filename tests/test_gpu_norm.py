@@ -1,0 +1,100 @@
+"""GPU parity of the UNet-block neighbours of the adapter sites: apx_groupnorm_nhwc / apx_add_bias_nhwc against
+the torch ops they replace (nn.GroupNorm + F.silu with the conv-bias / time-embedding adds in front; the ResnetBlock2D output add),
+and the channels-last route of the restated UNet against its stock NCHW graph."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ap_adapter_b200 import _lib
+
+from gpu_util import record, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("shape,extras,silu", [
+    ((2, 128, 250, 16), False, True),      # first resnet: 4 channels per group, 4000 pixels
+    ((2, 256, 250, 16), False, True),      # last up block's concatenated input: the largest group (128 KB of fp32)
+    ((2, 256, 125, 8), True, True),        # norm2 with conv1 bias + time embedding
+    ((2, 384, 63, 4), True, True),         # 12 channels per group
+    ((2, 640, 32, 2), False, False),       # Transformer2DModel.norm (no SiLU)
+    ((3, 1280, 32, 2), True, True),        # 40 channels per group (mid-level skip concat), odd batch
+    ((16, 256, 125, 8), True, True),       # BASELINE batch 8
+], ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
+def test_groupnorm_nhwc_matches_torch(shape, extras, silu, dtype):
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(c + h)
+    x = (torch.randn(shape, generator=g) * 2.0 + 0.5).to(dtype)
+    gamma, beta = 1.0 + 0.3 * torch.randn(c, generator=g), 0.3 * torch.randn(c, generator=g)
+    cb = 0.5 * torch.randn(c, generator=g) if extras else None
+    t = (0.7 * torch.randn(b, 2 * c, generator=g)).to(dtype)[:, c:] if extras else None          # a column slice (row stride 2c), as in the UNet
+    v = x.float()
+    if extras:
+        v = v + cb[None, :, None, None] + t.float()[:, :, None, None]
+    ref = F.group_norm(v, 32, gamma, beta, 1e-5)
+    ref = F.silu(ref) if silu else ref
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    n0 = _lib.launch_count()
+    y = _lib.groupnorm_nhwc(xc, gamma.cuda(), beta.cuda(), 32, 1e-5, silu, cb.cuda() if extras else None, t.cuda() if extras else None)
+    assert _lib.launch_count() - n0 == 1
+    assert y.shape == x.shape and y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    err = rel_err(y, ref)
+    record("groupnorm_nhwc/" + "x".join(map(str, shape)), dtype=str(dtype), err=err)
+    assert err < (1e-3 if dtype == torch.float16 else 8e-3)        # one 16-bit rounding of an O(1) value
+
+
+def test_groupnorm_rejects_what_it_does_not_cover():
+    x = torch.zeros(1, 96, 4, 4, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    w = torch.ones(96, device="cuda")
+    assert not _lib.groupnorm_nhwc_ok(16, 96, 32) and _lib.groupnorm_nhwc_ok(16, 128, 32) and not _lib.groupnorm_nhwc_ok(8000, 256, 32)
+    with pytest.raises(_lib.ApxError, match="multiple of 4"):
+        _lib.groupnorm_nhwc(x, w, w, 32, 1e-5, False)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_add_bias_nhwc_matches_torch(dtype):
+    g = torch.Generator().manual_seed(0)
+    a, b = (torch.randn(3, 384, 63, 4, generator=g).to(dtype) for _ in range(2))
+    bias = torch.randn(384, generator=g)
+    ref = (a.float() + b.float() + bias[None, :, None, None]) * 0.5
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)  # noqa: E731
+    y = _lib.add_bias_nhwc(cl(a), cl(b), bias.cuda(), 0.5)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(y, ref) < (1e-3 if dtype == torch.float16 else 8e-3)
+    assert rel_err(_lib.add_bias_nhwc(cl(a), cl(b), None), a.float() + b.float()) < (1e-3 if dtype == torch.float16 else 8e-3)
+
+
+def test_unet_channels_last_route_matches_stock_graph():
+    """One forward of the full-size restated UNet (fp16, 10 s latent, CFG batch 2): channels-last route vs the stock NCHW graph with
+    the same (libapx) processors.  Two fp16 evaluations of a 700 M-parameter network that differ in where they round."""
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from ap_adapter_b200.unet import NHWC, AudioLDM2UNet2DConditionModel, build_attn_processors
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval().half().cuda()
+    unet.set_attn_processor(build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=0.5, device="cuda", dtype=torch.float16))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(2, 8, 250, 16, generator=g, device="cuda", dtype=torch.float16)
+    kw = dict(encoder_hidden_states=torch.randn(2, 136, 768, generator=g, device="cuda", dtype=torch.float16),
+              encoder_hidden_states_1=torch.randn(2, 16, 1024, generator=g, device="cuda", dtype=torch.float16),
+              encoder_attention_mask_1=torch.ones(2, 16, device="cuda"))
+    t = torch.tensor(500, device="cuda")
+    saved = NHWC.enabled
+    try:
+        with torch.no_grad():
+            NHWC.enabled = False
+            n0 = _lib.launch_count()
+            y_stock = unet(x, t, **kw)[0]
+            n_stock = _lib.launch_count() - n0
+            NHWC.enabled = True
+            n0 = _lib.launch_count()
+            y = unet(x, t, **kw)[0]
+            n_nhwc = _lib.launch_count() - n0
+    finally:
+        NHWC.enabled = saved
+    # 44 resnet GroupNorms + 64 transformer GroupNorms + conv_norm_out, 22 resnet output adds
+    assert n_nhwc - n_stock == 109 + 22, (n_nhwc, n_stock)
+    assert y.shape == y_stock.shape and y.is_contiguous() and torch.isfinite(y).all()
+    err = rel_err(y, y_stock)
+    record("unet/channels_last_vs_stock", err=err)
+    assert err < 1e-2

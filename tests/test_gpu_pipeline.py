@@ -9,7 +9,7 @@ from ap_adapter_b200 import _lib
 from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
 from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
 from ap_adapter_b200.pipeline import APAdapterDenoiser
-from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
+from ap_adapter_b200.unet import NHWC, AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
 from oracle import audiomae_oracle, cases
 from oracle.ref_processors import OracleIPAttnProcessor2_0
 
@@ -64,13 +64,13 @@ def test_config3_end_to_end_matches_the_oracle_chain(world):
     record("config3/context", err=ctx_err)
     assert ctx_err < 1.5e-3                                      # AudioMAE with fp16 GEMM operands + fp16 context storage (measured 5.5e-4)
     unet.set_attn_processor(dict(theirs))
-    FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
+    FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
     try:
         ref_den = APAdapterDenoiser(unet)
         want = ref_den.denoise(cu(inp["lat"]).half(), cu(ctx).half(), cu(inp["pe"]).half(), cu(inp["mask"]),
                                num_inference_steps=200, guidance_scale=GUIDANCE, use_cuda_graph=False, steps_to_run=STEPS)
     finally:
-        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = True
+        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = NHWC.enabled = True
         BasicTransformerBlock.fold_residual = "ip"
         unet.set_attn_processor(dict(ours))
     err = rel_err(got, want)

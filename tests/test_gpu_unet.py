@@ -5,7 +5,7 @@ import torch
 from ap_adapter_b200 import _lib
 from ap_adapter_b200.attention_processor import AttnProcessor2_0, IPAttnProcessor2_0
 from ap_adapter_b200.pipeline import APAdapterDenoiser
-from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
+from ap_adapter_b200.unet import NHWC, AudioLDM2UNet2DConditionModel, BasicTransformerBlock, FeedForward, build_attn_processors
 from oracle.ref_processors import OracleIPAttnProcessor2_0
 
 from gpu_util import rel_err
@@ -51,11 +51,11 @@ def test_unet_step_matches_pytorch_processors(setup):
     with torch.no_grad():
         unet.set_attn_processor(dict(theirs))
         # the comparison graph is the stock one: torch FeedForward, torch processors with separate to_q / to_k / to_v GEMMs
-        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = False
+        FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
         try:
             y_ref = unet(x, torch.tensor(500, device="cuda"), **kw)[0]
         finally:
-            FeedForward.use_fused = AttnProcessor2_0.fuse_projections = True
+            FeedForward.use_fused = AttnProcessor2_0.fuse_projections = NHWC.enabled = True
             BasicTransformerBlock.fold_residual = "ip"
         unet.set_attn_processor(dict(ours))
         n0 = _lib.launch_count()
@@ -66,7 +66,7 @@ def test_unet_step_matches_pytorch_processors(setup):
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values())
     assert n_ff == 128 and n_plain == 224
-    assert launched >= _site_launches() + 2 * n_ff, launched
+    assert launched >= _site_launches() + 2 * n_ff + 109 + 22, launched     # + the channels-last route's GroupNorm / output-add kernels
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
     assert rel_err(y, y_ref) < 1e-2
@@ -88,7 +88,7 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     # residual GEMM is opt-in, APX_FOLD_RESIDUAL=1)
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values()) if BasicTransformerBlock.fold_residual is True else 0
-    assert per_step == _site_launches() + 2 * n_ff + n_plain
+    assert per_step == _site_launches() + 2 * n_ff + n_plain + 109 + 22     # sites, FeedForwards, channels-last GroupNorms / output adds
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)

@@ -316,3 +316,40 @@ def test_step_graph_key_covers_what_a_captured_step_bakes_in(tiny_unet):
     assert den._site_blobs() == [None] * (2 * len(adapters))
     den.invalidate_graph()
     assert den._graph is None
+
+
+def test_channels_last_route_is_the_same_function_as_the_stock_graph(tiny_unet, monkeypatch):
+    """The channels-last inference route of the restated UNet (NHWC: fused GroupNorm(+bias+temb)+SiLU, batched time-embedding
+    GEMM, proj_in / proj_out as linears on the free token view, shortcut + conv2 + biases in one add) computes what the stock NCHW
+    graph computes.  Run here on the CPU in fp32 with the two libapx kernels replaced by their torch statements, so the WIRING
+    (which bias goes where, slice offsets of the batched GEMM, views, memory formats) is what is tested; the kernels themselves
+    are pinned on the GPU (tests/test_gpu_unet.py)."""
+    from ap_adapter_b200 import _lib, unet as U
+
+    def add_bias(a, b, bias, scale=1.0):
+        y = a + b if bias is None else a + b + bias.to(a.dtype)[None, :, None, None]
+        return (y * scale).contiguous(memory_format=torch.channels_last)
+
+    monkeypatch.setattr(U.NHWC, "usable", staticmethod(lambda x: U.NHWC.enabled and not torch.is_grad_enabled()))
+    monkeypatch.setattr(_lib, "groupnorm_nhwc_ok", lambda hw, c, g: False)      # -> the torch statement inside _gn_nhwc
+    monkeypatch.setattr(_lib, "add_bias_nhwc", add_bias)
+    tiny_unet.set_attn_processor(build_attn_processors(tiny_unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=0.5))
+    torch.manual_seed(4)
+    for p in tiny_unet.parameters():            # non-trivial biases / affine parameters everywhere
+        if p.dim() == 1:
+            p.data.normal_(0.0, 0.3)
+    x = torch.randn(2, 8, 50, 16)               # 50 rows: the up path needs forward_upsample_size
+    kw = dict(encoder_hidden_states=torch.randn(2, 8 + 8, 768), encoder_hidden_states_1=torch.randn(2, 5, 1024),
+              encoder_attention_mask_1=torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1.0]]))
+    seen = []
+    hook = tiny_unet.mid_block.resnets[0].register_forward_hook(lambda m, i, o: seen.append(o.is_contiguous(memory_format=torch.channels_last)))
+    with torch.no_grad():
+        monkeypatch.setattr(U.NHWC, "enabled", False)
+        y_stock = tiny_unet(x, 321, **kw)[0]
+        monkeypatch.setattr(U.NHWC, "enabled", True)
+        y_nhwc = tiny_unet(x, 321, **kw)[0]
+    hook.remove()
+    assert seen == [False, True]                # the second forward really ran channels-last
+    assert y_nhwc.is_contiguous() and y_nhwc.shape == y_stock.shape
+    assert ((y_nhwc - y_stock).abs().max() / y_stock.abs().max()).item() < 1e-5
+    assert not U.NHWC.active and all("_temb_proj" not in r.__dict__ for r in tiny_unet._resnets())
