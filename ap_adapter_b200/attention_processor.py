@@ -69,9 +69,31 @@ class AttnProcessor2_0(nn.Module):
             return F.linear(hidden_states, self._cat_weight((attn.to_q, attn.to_k, attn.to_v))).chunk(3, dim=-1)
         query = attn.to_q(hidden_states)
         if fused and encoder_hidden_states.dtype == attn.to_k.weight.dtype:
-            key, value = F.linear(encoder_hidden_states, self._cat_weight((attn.to_k, attn.to_v))).chunk(2, dim=-1)
-            return query, key, value
+            # cross-attention context (T5 embeddings): K / V do not depend on the timestep — projected once per (context, weights)
+            # identity + version and reused by every denoise step, like the adapter sites' context cache
+            ws = (attn.to_k.weight, attn.to_v.weight)
+            ckey = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape),
+                    encoder_hidden_states.dtype) + tuple((w.data_ptr(), w._version) for w in ws)
+            c = getattr(self, "_kv", None)
+            if c is None or c[0] != ckey or c[3] is not encoder_hidden_states or any(a is not b for a, b in zip(c[4], ws)):
+                key, value = F.linear(encoder_hidden_states, self._cat_weight((attn.to_k, attn.to_v))).chunk(2, dim=-1)
+                c = self._kv = (ckey, key, value, encoder_hidden_states, ws)
+            return query, c[1], c[2]
         return query, attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)
+
+    def _mask(self, attn, attention_mask, sequence_length, batch_size):
+        """prepare_attention_mask + the per-head view (reference :245-249); cached per mask identity under inference: the T5
+        mask is the same tensor at every step and every site."""
+        if torch.is_grad_enabled() or not attention_mask.is_cuda:
+            m = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+            return m.view(batch_size, attn.heads, -1, m.shape[-1])
+        key = (attention_mask.data_ptr(), attention_mask._version, tuple(attention_mask.shape), attention_mask.dtype, sequence_length,
+               batch_size, attn.heads)
+        c = getattr(self, "_mk", None)
+        if c is None or c[0] != key or c[2] is not attention_mask:
+            m = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+            c = self._mk = (key, m.view(batch_size, attn.heads, -1, m.shape[-1]), attention_mask)
+        return c[1]
 
     accepts_residual = True   # __call__ takes `residual_inout` (the restated transformer block passes its residual stream)
 
@@ -95,8 +117,7 @@ class AttnProcessor2_0(nn.Module):
         batch_size, sequence_length, _ = (
             hidden_states.shape if encoder_hidden_states is None else encoder_hidden_states.shape)
         if attention_mask is not None:
-            attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
-            attention_mask = attention_mask.view(batch_size, attn.heads, -1, attention_mask.shape[-1])
+            attention_mask = self._mask(attn, attention_mask, sequence_length, batch_size)
         if attn.group_norm is not None:
             hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
 

@@ -75,12 +75,87 @@ def allreduce_adapter_grads(params: Iterable[nn.Parameter], group=None) -> int:
     return flat.numel() * 4
 
 
+class BucketedGradReducer:
+    """Data-parallel gradient averaging of the adapter weights, overlapped with the backward pass (what torch DDP does for the
+    reference run under accelerate, train_apadapter_v2.py:939-958): the 64 adapter gradients are grouped, in the order the backward
+    produces them (last site first), into buckets of ``bucket_bytes``; a post-accumulate-grad hook copies each gradient into its
+    bucket and, when a bucket is complete, issues ONE asynchronous ``all_reduce`` for it — NCCL runs it on its own stream over
+    NVLink while autograd is still computing the earlier sites.  ``finish()`` waits, divides by the world size and writes the
+    averages back into ``p.grad``.  Outside a process group (or with one rank) it does nothing."""
+
+    def __init__(self, params: Iterable[nn.Parameter], bucket_bytes: int = 25 << 20, group=None):
+        import torch.distributed as dist
+
+        self.group = group
+        self.params = list(params)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.buckets = []            # (flat fp32 buffer, [(param, offset, numel)])
+        self.slot = {}               # id(param) -> (bucket index, offset)
+        self.handles, self.pending, self.hooks = [], [], []
+        self.bytes_reduced = 0
+        if self.world == 1 or not self.params:
+            return
+        cur, cur_n = [], 0
+        for p in reversed(self.params):                       # backward order
+            if cur and (cur_n + p.numel()) * 4 > bucket_bytes:
+                self._close(cur, cur_n)
+                cur, cur_n = [], 0
+            cur.append((p, cur_n, p.numel()))
+            cur_n += p.numel()
+        if cur:
+            self._close(cur, cur_n)
+        for p in self.params:
+            self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _close(self, entries, n):
+        buf = torch.zeros(n, dtype=torch.float32, device=entries[0][0].device)
+        for p, off, _ in entries:
+            self.slot[id(p)] = (len(self.buckets), off)
+        self.buckets.append((buf, entries))
+        self.pending.append(len(entries))
+
+    def _on_grad(self, p):
+        import torch.distributed as dist
+
+        bi, off = self.slot[id(p)]
+        buf, entries = self.buckets[bi]
+        buf[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self.handles.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.bytes_reduced += buf.numel() * 4
+
+    def finish(self) -> int:
+        """Wait for the bucket all-reduces, average, write back.  Returns the bytes reduced in this step."""
+        if self.world == 1:
+            return 0
+        for h in self.handles:
+            h.wait()
+        for bi, (buf, entries) in enumerate(self.buckets):
+            if self.pending[bi] != 0:
+                continue            # a parameter of this bucket got no gradient this step: nothing was reduced for it
+            buf.div_(self.world)
+            for p, off, n in entries:
+                p.grad.copy_(buf[off:off + n].view_as(p.grad))
+        done = self.bytes_reduced
+        self.handles, self.bytes_reduced = [], 0
+        self.pending = [len(e) for _, e in self.buckets]
+        return done
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
 def train_step(unet: nn.Module, scheduler: DDIMScheduler, optimizer: torch.optim.Optimizer, latents: torch.Tensor,
                generated_prompt_embeds: torch.Tensor, prompt_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor],
                max_grad_norm: float = 1.0, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, generator=None,
-               params: Optional[List[nn.Parameter]] = None, group=None) -> float:
+               params: Optional[List[nn.Parameter]] = None, group=None, reducer: Optional[BucketedGradReducer] = None) -> float:
     """One optimiser step (train_apadapter_v2.py:895-979).  ``latents`` (B, 8, T/4, 16) stand for ``vae.encode(mel) * scaling``;
-    ``generated_prompt_embeds`` (B, 8 + La, 768) already carries the AudioMAE tokens behind the 8 text tokens.  Returns the loss."""
+    ``generated_prompt_embeds`` (B, 8 + La, 768) already carries the AudioMAE tokens behind the 8 text tokens.  ``reducer`` (a
+    ``BucketedGradReducer`` over ``params``) overlaps the gradient all-reduce with the backward; without it the gradients are
+    reduced in one flat all-reduce after the backward.  Returns the loss."""
     params = adapter_parameters(unet) if params is None else params
     noise = torch.randn(latents.shape, generator=generator, device=latents.device, dtype=latents.dtype)
     timesteps = torch.randint(0, scheduler.num_train_timesteps, (latents.shape[0],), generator=generator,
@@ -98,7 +173,10 @@ def train_step(unet: nn.Module, scheduler: DDIMScheduler, optimizer: torch.optim
     loss = F.mse_loss(pred.float(), target.float(), reduction="mean")
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
-    allreduce_adapter_grads(params, group)
+    if reducer is not None:
+        reducer.finish()          # the bucket all-reduces were issued from autograd hooks during backward()
+    else:
+        allreduce_adapter_grads(params, group)
     if max_grad_norm is not None:
         torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
     optimizer.step()

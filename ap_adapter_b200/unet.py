@@ -693,10 +693,8 @@ class AudioLDM2UNet2DConditionModel(nn.Module):
                 attention_mask=None, cross_attention_kwargs=None, encoder_attention_mask=None, return_dict: bool = False,
                 encoder_hidden_states_1=None, encoder_attention_mask_1=None):
         forward_upsample_size = any(s % (2 ** self.num_upsamplers) != 0 for s in sample.shape[-2:])
-        if encoder_attention_mask is not None:
-            encoder_attention_mask = ((1 - encoder_attention_mask.to(sample.dtype)) * -10000.0).unsqueeze(1)
-        if encoder_attention_mask_1 is not None:
-            encoder_attention_mask_1 = ((1 - encoder_attention_mask_1.to(sample.dtype)) * -10000.0).unsqueeze(1)
+        encoder_attention_mask = self._additive_mask(encoder_attention_mask, sample.dtype, "m0")
+        encoder_attention_mask_1 = self._additive_mask(encoder_attention_mask_1, sample.dtype, "m1")
 
         timesteps = timestep
         if not torch.is_tensor(timesteps):
@@ -719,6 +717,20 @@ class AudioLDM2UNet2DConditionModel(nn.Module):
                     r.__dict__.pop("_temb_proj", None)
         return self._forward_trunk(sample, emb, encoder_hidden_states, attention_mask, cross_attention_kwargs, encoder_attention_mask,
                                    encoder_hidden_states_1, encoder_attention_mask_1, forward_upsample_size, return_dict)
+
+    def _additive_mask(self, mask, dtype, tag):
+        """(B, L) keep-mask -> additive (B, 1, L) bias (modeling_audioldm2.py:741-747).  Under inference the result is cached per mask
+        identity + version, so every step hands the processors the SAME tensor and their per-site mask caches hit."""
+        if mask is None:
+            return None
+        if torch.is_grad_enabled():
+            return ((1 - mask.to(dtype)) * -10000.0).unsqueeze(1)
+        cache = self.__dict__.setdefault(_CACHE_ATTR, {})
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, dtype)
+        hit = cache.get(tag)
+        if hit is None or hit[0] != key or hit[2] is not mask:
+            hit = cache[tag] = (key, ((1 - mask.to(dtype)) * -10000.0).unsqueeze(1), mask)
+        return hit[1]
 
     def _resnets(self):
         r = self.__dict__.get("_resnet_list")

@@ -39,20 +39,48 @@ LAT_SHAPE = (8, 250, 16)
 INFER_STEPS = 200
 GUIDANCE = 7.5
 AP_SCALE = 0.5
+WORKLOAD = "step"
+WORKLOAD_NAME = ("BASELINE configs[1]: AudioLDM2-large UNet single denoise step (CFG, DDIM-200 schedule) with AP "
+                 "attn2 processors at 32 sites, 10 s latent (8x250x16)")
+
+
+def set_workload(name: str, args) -> None:
+    """`step` (default) = BASELINE configs[1], the configuration the metric is quoted on.  The other presets re-parameterise the same
+    step loop (config4) or time a different unit of work (config3: one whole generation; train: one optimiser step); they are run
+    by hand / by tools/gpu_visit.sh and their lines are committed under profiles/, the driver's round-end line stays `step`."""
+    global LA, AP_SCALE, GUIDANCE, WORKLOAD, WORKLOAD_NAME
+    WORKLOAD = name
+    if name == "config4":      # style_transfer preset (reference config.py:30-33): pooling 4x4 -> 32 audio tokens, ap_scale 0.55, g 9.5
+        LA, AP_SCALE, GUIDANCE = 32, 0.55, 9.5
+        if args.batch == 1:
+            args.batch = 4     # 32 clips over 8 GPUs
+        WORKLOAD_NAME = ("BASELINE configs[3]: style_transfer preset, batch sharded data-parallel (4 clips per GPU), UNet denoise step with AP "
+                         "attn2 processors, 10 s latent (8x250x16); NCCL gather of the final latents only")
+    elif name == "config3":
+        if args.batch == 1:
+            args.batch = 4
+        WORKLOAD_NAME = ("BASELINE configs[2]: full timbre_transfer inference, AudioMAE encode (mel + zero mel) + context K/V caches + 200 "
+                         "CUDA-graphed CFG/DDIM steps, batch 4, through APAdapterDenoiser.__call__ (host mel in, host latents out)")
+    elif name == "train":
+        if args.batch == 1:
+            args.batch = 4
+        WORKLOAD_NAME = ("BASELINE configs[4]: one adapter-training optimiser step (train_apadapter_v2.py:892-979), bf16 autocast, fp32 adapter "
+                         "weights, adapter-only gradients, 4 clips per GPU, bucketed NCCL all-reduce overlapped with the backward")
 
 
 def workload_config(batch: int, n_gpus: int) -> dict:
-    return {"workload": "BASELINE configs[1]: AudioLDM2-large UNet single denoise step (CFG, DDIM-200 schedule) with AP "
-                        "attn2 processors at 32 sites, 10 s latent (8x250x16)",
+    return {"workload": WORKLOAD_NAME,
             "clips_per_gpu": batch, "cfg_batch_per_gpu": 2 * batch, "text_tokens": LT, "audio_tokens": LA,
             "t5_tokens": L_T5, "ap_scale": AP_SCALE, "guidance_scale": GUIDANCE, "ddim_steps": INFER_STEPS,
             "parallelism": f"clips sharded over {n_gpus} rank(s), no data-path collective, final all-gather of latents",
             "l2": "per-step working set (1.4 GB of fp16 UNet weights) exceeds the 126 MB L2; no flush needed"}
 
 
-HOST_GRAPH = ("adapter sites: libapx (site kernel / 3-kernel form, residual add folded in); GEGLU FeedForwards: 2 libapx GEMMs with "
-              "GEGLU / residual epilogues; plain attention sites: fused QKV (KV) projection on cuBLAS + cuDNN SDPA; everything else "
-              "stock PyTorch ops; one CUDA graph per step")
+HOST_GRAPH = ("adapter sites: libapx (all-heads site kernel at C=256, one-head cluster site kernel at C=384, 3-kernel form at C=640; residual "
+              "add folded in); GEGLU FeedForwards: 2 libapx GEMMs with GEGLU / residual epilogues; convolutional trunk channels-last with "
+              "libapx GroupNorm(+conv bias + time embedding)+SiLU and ResnetBlock output-add kernels, proj_in / proj_out as linears on the "
+              "token view, one GEMM for all time-embedding projections; plain attention sites: fused QKV projection on cuBLAS + cuDNN SDPA, "
+              "T5 K/V projected once per context; one CUDA graph per step")
 
 
 def peaks() -> dict:
@@ -241,7 +269,8 @@ def site_roofline(batch: int, iters: int = 30) -> dict:
         pass
     return {"kernel": f"{name} via apx_ipattn_fwd ({launches_per_call} launch(es)/call), Bc={bc} S={s} C={c} H={h} Lt={LT} La={LA} fp16",
             "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4),
-            "traffic": traffic, "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
+            "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this launch; not re-measured by this run)",
+            "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
             "floor_us": round(1e6 * max(t_tensor, t_hbm), 3), "peak_source": pk["source"], "operand_copies_rotated": r}
 
 
@@ -283,6 +312,162 @@ def audiomae_timing(iters: int = 20) -> dict:
     return out
 
 
+def clip_inputs(clips, dev):
+    """Synthetic inputs of the given GLOBAL clip indices (one generator per clip, so any rank can rebuild any clip's inputs):
+    latents (n, 8, 250, 16), [uncond; cond] 768-d context (2n, Lt + La, 768), T5 context (2n, 16, 1024), T5 mask (2n, 16)."""
+    lat, g_u, g_c, p_u, p_c = [], [], [], [], []
+    for c in clips:
+        g = torch.Generator(device=dev).manual_seed(1000 + c)
+        lat.append(torch.randn(1, *LAT_SHAPE, generator=g, device=dev, dtype=torch.float16))
+        ctx = torch.randn(2, LT + LA, 768, generator=g, device=dev, dtype=torch.float16)
+        t5 = torch.randn(2, L_T5, 1024, generator=g, device=dev, dtype=torch.float16)
+        g_u.append(ctx[:1]); g_c.append(ctx[1:]); p_u.append(t5[:1]); p_c.append(t5[1:])
+    n = len(lat)
+    return (torch.cat(lat), torch.cat(g_u + g_c).contiguous(), torch.cat(p_u + p_c).contiguous(), torch.ones(2 * n, L_T5, device=dev))
+
+
+def shard_equality_check(den, graph, gathered, b, world, rank, dev, ts, coefs, steps) -> dict:
+    """SURVEY.md §4 item 4 on hardware: the gathered latents of the N-rank run must equal what ONE rank computes for the same clips.
+    Rank 0 rebuilds the inputs of the LAST rank's clips, runs the same `steps` denoise steps through its own step graph and compares
+    them with the rows the all-gather delivered (every rank runs the comparison on the shard after its own, so a bad rank cannot hide)."""
+    import torch.distributed as dist
+    other = (rank + 1) % world
+    lat0, gpe, pe, mask = clip_inputs(range(other * b, (other + 1) * b), dev)
+    g2 = den._step_graph(lat0, gpe, pe, mask, GUIDANCE)
+    g2["latents"].copy_(lat0)
+    for i in range(steps):
+        g2["t"].copy_(ts[i % INFER_STEPS]); g2["coef"].copy_(coefs[i % INFER_STEPS])
+        g2["graph"].replay()
+        g2["latents"].copy_(g2["out"])
+    mine = g2["latents"].float()
+    theirs = gathered[other * b:(other + 1) * b].float()
+    diff = ((mine - theirs).abs().max() / theirs.abs().max().clamp_min(1e-30)).item()
+    stat = torch.tensor([diff, 0.0 if torch.equal(mine, theirs) else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    ok = stat[0].item() <= 1e-3
+    assert ok, f"sharded run differs from the single-rank recomputation: max rel diff {stat[0].item():.3e}"
+    return {"what": f"every rank recomputed the next rank's {b} clip(s) for {steps} steps and compared with the all-gathered rows",
+            "max_rel_diff": stat[0].item(), "bitwise_equal_on_all_ranks": stat[1].item() == 0.0, "bar": 1e-3}
+
+
+def run_config3(b, unet, dev, iters=1) -> dict:
+    """BASELINE configs[2]: mel (host) -> AudioMAE(mel) + AudioMAE(0) -> context -> K/V caches -> 200 graphed CFG/DDIM steps ->
+    latents (host), batch `b`, through APAdapterDenoiser.__call__.  AudioMAE is random-init (no checkpoint offline)."""
+    from ap_adapter_b200.audiomae import AudioMAEConditionCTPoolRand
+    from ap_adapter_b200.pipeline import APAdapterDenoiser
+    torch.manual_seed(0)
+    mae = AudioMAEConditionCTPoolRand(checkpoint_path=None).to(dev).eval()
+    den = APAdapterDenoiser(unet, mae)
+    g = torch.Generator().manual_seed(5)
+    mel = (torch.randn(1, 1024, 128, generator=g) * 0.45 - 0.45).pin_memory()
+    gpe8 = torch.randn(2 * b, LT, 768, generator=g).half().pin_memory()
+    pe = torch.randn(2 * b, L_T5, 1024, generator=g).half().pin_memory()
+    mask = torch.ones(2 * b, L_T5).pin_memory()
+    lat = torch.randn(b, *LAT_SHAPE, generator=g).half().pin_memory()
+    out_h = torch.empty(b, *LAT_SHAPE, dtype=torch.float16).pin_memory()
+
+    def generate():
+        o = den(mel.to(dev, non_blocking=True), pe.to(dev, non_blocking=True), mask.to(dev, non_blocking=True),
+                gpe8.to(dev, non_blocking=True), time_pooling=2, freq_pooling=2, num_inference_steps=INFER_STEPS, guidance_scale=GUIDANCE,
+                audio_length_in_s=10.0, latents=lat.to(dev, non_blocking=True))
+        out_h.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        generate()                                   # first call: captures the step graph, builds caches
+        first = time.perf_counter() - t0
+        times = []
+        for _ in range(iters):
+            den.invalidate_graph()                   # a NEW prompt: context caches + graph are rebuilt, as for every new generation
+            t0 = time.perf_counter()
+            generate()
+            times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        generate()                                   # the same prompt again: graph and caches are reused
+        reuse = time.perf_counter() - t0
+    assert torch.isfinite(out_h).all()
+    sec = sum(times) / len(times)
+    return {"clips": b, "ddim_steps": INFER_STEPS, "time_pooling": 2, "freq_pooling": 2, "seconds_per_generation": round(sec, 4),
+            "steps_per_s": round(b * INFER_STEPS / sec, 2), "seconds_first_call": round(first, 3),
+            "seconds_per_generation_graph_reused": round(reuse, 4), "steps_per_s_graph_reused": round(b * INFER_STEPS / reuse, 2),
+            "what": "wall clock, host mel/embeddings/latents in, host latents out; includes 2 AudioMAE encodes on the first use of a pooling, "
+                    "32 context K/V cache builds, graph capture (new prompt) and 200 replays"}
+
+
+def run_train(args) -> dict:
+    """BASELINE configs[4]: one optimiser step of adapter training per 'step' (see training.train_step), data parallel."""
+    import torch.distributed as dist
+
+    from ap_adapter_b200 import _lib, training
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from ap_adapter_b200.pipeline import DDIMScheduler
+    from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.batch
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval().to(dev, torch.bfloat16)           # frozen UNet in the mixed-precision dtype
+    procs = build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=1.0, device=dev, dtype=torch.float32)   # fp32 adapter weights
+    unet.set_attn_processor(dict(procs))
+    params = training.freeze_all_but_adapter(unet)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2)
+    red = training.BucketedGradReducer(params) if world > 1 else None
+    sched = DDIMScheduler()
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    lat = torch.randn(b, *LAT_SHAPE, generator=g, device=dev, dtype=torch.bfloat16)
+    la_cycle = [512, 128, 32, 8]                                                   # pooling rate drawn from [1, 2, 4, 8] (train_apadapter_v2.py:445-446)
+    ctxs = [torch.randn(b, LT + la, 768, generator=g, device=dev, dtype=torch.bfloat16) for la in la_cycle]
+    pe = torch.randn(b, L_T5, 1024, generator=g, device=dev, dtype=torch.bfloat16)
+    mask = torch.ones(b, L_T5, device=dev)
+
+    def step(i):
+        return training.train_step(unet, sched, opt, lat, ctxs[i % 4], pe, mask, generator=g, params=params, reducer=red)
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    loss = 0.0
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        w = torch.cat([p.detach().reshape(-1)[:1024] for p in params])
+        ws = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(ws, w)
+        assert all(torch.equal(ws[0], x) for x in ws), "replicas diverged"
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    return {"metric": "adapter_train_steps_per_s", "value": args.steps / (ms * 1e-3), "unit": "optimiser steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init UNet / adapter weights, N(0,1) latents and contexts)",
+            "config": dict(workload_config(b, world), effective_batch=b * world, audio_tokens="cycled 512/128/32/8",
+                           all_reduce_bytes_per_step=sum(p.numel() for p in params) * 4 if world > 1 else 0,
+                           all_reduce="bucketed (25 MB), issued from autograd hooks, overlapped with the backward (training.BucketedGradReducer)"),
+            "impl": "ours", "gpu_launches": launches, "final_loss": loss, "replicas_bitwise_equal": True if world > 1 else None}
+
+
 def run_ours(args) -> dict:
     import torch.distributed as dist
 
@@ -309,11 +494,7 @@ def run_ours(args) -> dict:
     ours = build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
     unet.set_attn_processor(dict(ours))
     den = APAdapterDenoiser(unet)
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
-    lat0 = torch.randn(b, *LAT_SHAPE, generator=g, device=dev, dtype=torch.float16)
-    gpe = torch.randn(2 * b, LT + LA, 768, generator=g, device=dev, dtype=torch.float16)
-    pe = torch.randn(2 * b, L_T5, 1024, generator=g, device=dev, dtype=torch.float16)
-    mask = torch.ones(2 * b, L_T5, device=dev)
+    lat0, gpe, pe, mask = clip_inputs(range(rank * b, (rank + 1) * b), dev)
     den.scheduler.set_timesteps(INFER_STEPS, device=dev)
     ts, coefs = den.scheduler.timesteps, den.scheduler.coefficients(dev)
 
@@ -338,19 +519,28 @@ def run_ours(args) -> dict:
             step(i)
         graph["latents"].copy_(lat0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        final = gather_latents(graph["latents"], world * b) if world > 1 else graph["latents"]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        assert torch.isfinite(final).all(), "non-finite latents"
+        # Clocks under load: nvidia-smi polling costs the polled GPU several per cent (round 1: the sampled loop read 8 % slower than
+        # the unsampled one), so the sampler runs over an IDENTICAL UNTIMED repeat of the loop, not over the timed regions.
+        graph["latents"].copy_(lat0)
         with ClockSampler(local) as clk:
             barrier()
             w0 = time.perf_counter()
-            e0.record()
-            for i in range(args.steps):
+            for i in range(max(args.steps, int(1500 / max(ms / args.steps, 1e-3)))):   # >= 1.5 s under load: several 200 ms samples
                 step(i)
-            final = gather_latents(graph["latents"], world * b) if world > 1 else graph["latents"]
-            e1.record()
             barrier()
             w1 = time.perf_counter()
-        ms = e0.elapsed_time(e1)
-        assert torch.isfinite(final).all(), "non-finite latents"
         clocks = clk.summary(w0, w1)
+        clocks["sampled"] = "during an identical untimed repeat of the timed loop (polling perturbs the polled GPU)"
+        shard_check = shard_equality_check(den, graph, final, b, world, rank, dev, ts, coefs, args.steps) if world > 1 else None
 
         # ---- end to end: the step's latents come from and go back to pinned host memory every step ------------------
         h_lat = lat0.cpu().pin_memory()
@@ -394,13 +584,20 @@ def run_ours(args) -> dict:
         "gpu_launches": per_step_launches * args.steps, "gpu_launches_per_step": per_step_launches,
         "clocks": clocks,
     }
-    if rank == 0:
+    if shard_check is not None:
+        out["shard_check"] = shard_check
+    if rank == 0 and WORKLOAD == "step":
         out["roofline"] = site_roofline(b)
         out["audiomae"] = audiomae_timing()
         try:   # the fair same-box comparison; informational, never allowed to break the bench line
             out["torch_gpu"] = torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps=min(args.steps, 50))
         except Exception as exc:  # noqa: BLE001
             out["torch_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if world == 1 and not args.no_cpu_baseline and not args.no_extras:
+            try:   # BASELINE configs[2] as one path (informational beside the headline; its own line: --workload config3)
+                out["config3"] = run_config3(4, unet, dev, iters=1)
+            except Exception as exc:  # noqa: BLE001
+                out["config3"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(b, steps=3, warmup=1, budget_s=25.0)
     if world > 1:
@@ -482,15 +679,39 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
         unet.set_attn_processor(dict(ours))
 
 
+def run_config3_line(args) -> dict:
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    unet = AudioLDM2UNet2DConditionModel().eval().half().to(dev)
+    unet.set_attn_processor(dict(build_attn_processors(unet, IPAttnProcessor2_0, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)))
+    r = run_config3(args.batch, unet, dev, iters=2)
+    return {"metric": METRIC, "value": r["steps_per_s"], "unit": UNIT, "n_gpus": 1, "steps": INFER_STEPS, "warmup": 1,
+            "ms_per_step": 1e3 * r["seconds_per_generation"] / INFER_STEPS, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic (random-init UNet / AudioMAE / adapter weights, N(-0.45, 0.45) mel, N(0,1) latents and contexts)",
+            "config": workload_config(args.batch, 1), "impl": "ours", "e2e": {"value": r["steps_per_s"], "unit": UNIT,
+            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "host tensors in / out once per GENERATION (200 steps), see config3"},
+            "config3": r}
+
+
 def run_reference(args) -> dict:
+    """The reference's CPU path on the host cores.  Under torchrun only rank 0 works; it then runs the WHOLE job's clips (n_gpus x
+    clips_per_gpu) so that its line describes the same workload as the N-GPU arm (the host does not get faster with more GPUs)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    r = cpu_reference(args.batch, steps=args.steps, warmup=max(1, min(args.warmup, 2)), budget_s=150.0)
+    if args.workload not in ("step", "config4"):
+        return {"impl": "reference", "metric": METRIC, "value": None, "unit": UNIT, "n_gpus": args.gpus,
+                "declined": f"the CPU arm times the denoise step (workloads step / config4), not '{args.workload}'"}
+    n = max(1, args.gpus)
+    r = cpu_reference(args.batch * n, steps=args.steps, warmup=max(1, min(args.warmup, 2)), budget_s=150.0)
     return {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_timed"],
             "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (random-init UNet / adapter weights, N(0,1) latents and contexts)",
-            "config": workload_config(args.batch, 1), "impl": "reference",
+            "config": dict(workload_config(args.batch, n), host_arm=f"one host process runs all {args.batch * n} clip(s) of the {n}-GPU job"),
+            "impl": "reference",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -504,8 +725,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="clips per GPU (CFG doubles it inside the UNet)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational config3 leg of the default workload")
+    ap.add_argument("--workload", default="step", choices=["step", "config3", "config4", "train"])
     args = ap.parse_args()
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    set_workload(args.workload, args)
+    if args.impl == "reference":
+        out = run_reference(args)
+    elif args.workload == "train":
+        out = run_train(args)
+    elif args.workload == "config3":
+        out = run_config3_line(args)
+    else:
+        out = run_ours(args)
     if out is not None:
         print(json.dumps(out), flush=True)
 

@@ -9,7 +9,7 @@ from oracle import cases, ipattn_oracle, ref_shims
 # bar there is the reference's own bf16 path — the same algorithm run by stock PyTorch ops in bf16 on the same GPU
 # (`torch_lowp_site`): ours must be no further from the fp32 oracle than BF16_SLACK x that measured distance (see
 # `site_within_bar`), and every measured pair is written to gpurun_out/measured_errors.jsonl -> profiles/.
-TOL = {torch.float16: 1e-3, torch.bfloat16: 6e-3}   # bf16 cap: 1.25 x the largest stock-bf16 distance measured (profiles/r2a_measured_errors.jsonl: 4.7e-3)
+TOL = {torch.float16: 1e-3, torch.bfloat16: 6e-3}   # bf16 cap: 1.25 x the largest stock-bf16 distance measured (profiles/r2_measured_errors.jsonl: 4.7e-3)
 BF16_SLACK = 1.25
 
 

@@ -15,7 +15,7 @@ from gpu_util import record, rel_err
 pytestmark = pytest.mark.gpu
 
 # fp16 tensor-core operands with fp32 accumulation / residual stream / LayerNorm over 12 blocks: measured 5.9e-4 (synthetic mel) /
-# 6.8e-4 (piano.wav fbank) against the reference's own fp32 output (profiles/r2a_measured_errors.jsonl); the bar is 2x that.
+# 6.8e-4 (piano.wav fbank) against the reference's own fp32 output (profiles/r2_measured_errors.jsonl); the bar is 2x that.
 ENC_TOL = 1.4e-3
 
 

@@ -247,7 +247,7 @@ def test_adapter_backward_matches_autograd_of_the_oracle(shape, dtype):
     """dX, d to_k_ip.weight, d to_v_ip.weight from apx_ipattn_bwd against torch autograd through the fp32 oracle evaluated on
     the same 16-bit-rounded operands, for a random upstream gradient.  The backward chains five 16-bit roundings (Q, dO, P
     recomputed from 16-bit K, dQ, dX); measured max over the seven shapes: 9.4e-4 (fp16) / 6.1e-3 (bf16)
-    (profiles/r2a_measured_errors.jsonl) -> the bar is 2x that: 2e-3 / 1.2e-2."""
+    (profiles/r2_measured_errors.jsonl) -> the bar is 2x that: 2e-3 / 1.2e-2."""
     from oracle import ipattn_oracle
 
     bc, s, c, h, lt, la = shape
