@@ -45,6 +45,9 @@ class AttnProcessor2_0(nn.Module):
     # inference on CUDA: to_q/to_k/to_v of a self-attention site (to_k/to_v of a cross-attention site) run as ONE projection over
     # the concatenated weight (what diffusers' fuse_qkv_projections() does); APX_QKV_FUSED=0 keeps the three separate GEMMs
     fuse_projections = os.environ.get("APX_QKV_FUSED", "1") != "0"
+    # inference on CUDA: prepared attention masks (and, with fuse_projections, the K / V of a cross-attention context) are cached per
+    # tensor identity + version instead of being rebuilt at every site and step; False = rebuild every call, as the reference does
+    cache_context = True
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
@@ -74,7 +77,7 @@ class AttnProcessor2_0(nn.Module):
             ws = (attn.to_k.weight, attn.to_v.weight)
             ckey = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape),
                     encoder_hidden_states.dtype) + tuple((w.data_ptr(), w._version) for w in ws)
-            c = getattr(self, "_kv", None)
+            c = getattr(self, "_kv", None) if self.cache_context else None
             if c is None or c[0] != ckey or c[3] is not encoder_hidden_states or any(a is not b for a, b in zip(c[4], ws)):
                 key, value = F.linear(encoder_hidden_states, self._cat_weight((attn.to_k, attn.to_v))).chunk(2, dim=-1)
                 c = self._kv = (ckey, key, value, encoder_hidden_states, ws)
@@ -84,7 +87,7 @@ class AttnProcessor2_0(nn.Module):
     def _mask(self, attn, attention_mask, sequence_length, batch_size):
         """prepare_attention_mask + the per-head view (reference :245-249); cached per mask identity under inference: the T5
         mask is the same tensor at every step and every site."""
-        if torch.is_grad_enabled() or not attention_mask.is_cuda:
+        if torch.is_grad_enabled() or not attention_mask.is_cuda or not self.cache_context:
             m = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
             return m.view(batch_size, attn.heads, -1, m.shape[-1])
         key = (attention_mask.data_ptr(), attention_mask._version, tuple(attention_mask.shape), attention_mask.dtype, sequence_length,

@@ -723,7 +723,7 @@ class AudioLDM2UNet2DConditionModel(nn.Module):
         identity + version, so every step hands the processors the SAME tensor and their per-site mask caches hit."""
         if mask is None:
             return None
-        if torch.is_grad_enabled():
+        if torch.is_grad_enabled() or not AttnProcessor2_0.cache_context:
             return ((1 - mask.to(dtype)) * -10000.0).unsqueeze(1)
         cache = self.__dict__.setdefault(_CACHE_ATTR, {})
         key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype, dtype)

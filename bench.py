@@ -640,10 +640,11 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
     from ap_adapter_b200.attention_processor import AttnProcessor2_0
     from ap_adapter_b200.pipeline import APAdapterDenoiser
     from ap_adapter_b200.unet import NHWC, BasicTransformerBlock, FeedForward, build_attn_processors
-    saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled)
+    saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled, AttnProcessor2_0.cache_context)
     dev = lat0.device
     try:
         FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
+        AttnProcessor2_0.cache_context = False
         theirs = build_attn_processors(unet, _TorchIPAttnSite, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
         for k, p in ours.items():
             if hasattr(p, "to_k_ip"):
@@ -675,7 +676,8 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
                 "what": "same step, stock PyTorch graph on the same GPU: reference-algorithm processors (cuBLAS + cuDNN SDPA, fp16), "
                         "unfused FeedForward / projections / residual adds, one CUDA graph per step, device-timed"}
     finally:
-        FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled = saved
+        (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled,
+         AttnProcessor2_0.cache_context) = saved
         unet.set_attn_processor(dict(ours))
 
 
