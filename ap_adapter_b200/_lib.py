@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libapx.so")
 APX_F16, APX_BF16, APX_F32 = 0, 1, 2
 APX_EPI_NONE, APX_EPI_GELU, APX_EPI_GEGLU, APX_EPI_RES16 = 0, 1, 2, 4
 APX_IMPL_TC, APX_IMPL_SIMT, APX_IMPL_TC_UNFUSED = 0, 1, 2
-APX_SITE_AUTO, APX_SITE_ALLHEADS, APX_SITE_ONEHEAD = 0, 1, 2
+APX_SITE_AUTO, APX_SITE_ALLHEADS, APX_SITE_ONEHEAD, APX_SITE_ALLHEADS4 = 0, 1, 2, 3
 
 # every symbol include/apx.h declares: (restype, argtypes)
 _P, _I, _L, _F, _Z = c_void_p, c_int, c_int64, c_float, c_size_t

@@ -221,7 +221,8 @@ static bool site_kernel_enabled() {
 }
 static std::atomic<int> g_site_variant{[] { const char* e = getenv("APX_SITE_VARIANT"); return e ? atoi(e) : 0; }()};
 
-// Which fused kernel runs a site call: 0 = none (three kernels), 1 = all heads per CTA, 2 = one head per CTA (cluster of H).
+// Which fused kernel runs a site call: 0 = none (three kernels), 1 = all heads per CTA, 2 = one head per CTA (cluster of H),
+// 3 = all heads per CTA with four softmax warpgroups (full grids, 16 + 128 padded context columns).
 // Measured on B200 (profiles/r2d_harness_sites.txt, us per call, CUDA-graph replay):
 //   C=256 (2x1000, La=128): all-heads 12.6, one-head 27.3, three kernels 18.7     C=256 x16: 21.2 / 125 / 47
 //   C=384 (2x252):          one-head 18.6, three kernels 19.4                      C=384 x16: 51 / 24.7
@@ -235,8 +236,13 @@ static int pick_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
     const bool all_ok = site_geom(C, H).ok && ipattn_site_supported(C, H, Lt, La);
     const bool h1_ok = ipattn_site_h1_supported(C, H, Lt, La);
     const int forced = g_site_variant.load(std::memory_order_relaxed);
+    // four softmax warpgroups (score rows split over two threads): measured NO faster than two at Bc = 16 (23.0 vs 21.2 us,
+    // profiles/r2h_site4_trace.txt: the exp2 passes of the two head slots saturate the MUFU pipe whenever they overlap, and the
+    // per-head hand-off chain P -> P·V -> O -> next P bounds the rest) — kept as an opt-in variant (APX_SITE_ALLHEADS4), never auto-picked
+    const bool four_ok = all_ok && ipattn_site4_supported(C, H, Lt, La);
     if (forced == APX_SITE_ALLHEADS) return all_ok ? 1 : 0;
     if (forced == APX_SITE_ONEHEAD) return h1_ok ? 2 : 0;
+    if (forced == APX_SITE_ALLHEADS4) return four_ok ? 3 : 0;
     if (all_ok) return 1;
     if (!h1_ok) return 0;
     const H1Geom g = h1_geom(C, H);
@@ -265,7 +271,7 @@ int apx_ipattn_fused_ok(int C, int H, int Lt, int La) {
     return (ipattn_site_supported(C, H, Lt, La) || ipattn_site_h1_supported(C, H, Lt, La)) ? 1 : 0;
 }
 int apx_set_site_variant(int variant) {
-    APX_REQUIRE(variant == APX_SITE_AUTO || variant == APX_SITE_ALLHEADS || variant == APX_SITE_ONEHEAD, APX_EINVAL,
+    APX_REQUIRE(variant == APX_SITE_AUTO || variant == APX_SITE_ALLHEADS || variant == APX_SITE_ONEHEAD || variant == APX_SITE_ALLHEADS4, APX_EINVAL,
                 "apx_set_site_variant: unknown variant %d", variant);
     g_site_variant.store(variant);
     return APX_OK;
@@ -292,6 +298,9 @@ static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, con
         if (which == 1)
             return ipattn_site(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
                                La, ap_scale, dtype, accumulate, st);
+        if (which == 3)
+            return ipattn_site4(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt, La, ap_scale,
+                                dtype, accumulate, st);
         if (which == 2)
             return ipattn_site_h1(X, static_cast<const uint8_t*>(wpack) + pl.h1_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
                                   La, ap_scale, dtype, accumulate, st);

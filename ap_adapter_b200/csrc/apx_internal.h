@@ -78,6 +78,13 @@ struct SiteGeom {
     size_t wq_off[3], wo_off[3], total; // weight-pack sections per cluster size
 };
 SiteGeom site_geom(int C, int H);
+// shared-memory plan of the all-heads kernels for one (geometry, context, cluster size)
+struct SitePlan {
+    bool ok;
+    int nk, nv, n_wo, wo_early;
+    uint32_t off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, smem_bytes, wo_off[4];
+};
+SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs);
 bool ipattn_site_supported(int C, int H, int Lt, int La);
 int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
@@ -94,6 +101,10 @@ int ipattn_site_h1_pack_weights(const void* Wq, const void* Wo, void* pack, int 
 int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C, int H,
                    int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
 int ipattn_site_pick_cluster(int Bc, int S, int C, int H);
+// all-heads kernel with FOUR softmax warpgroups (apx_ipattn_site4.cu): 16 text-padded + 128 audio-padded columns, no cluster
+bool ipattn_site4_supported(int C, int H, int Lt, int La);
+int ipattn_site4(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C, int H,
+                 int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
 
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,

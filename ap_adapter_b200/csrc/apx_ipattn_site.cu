@@ -599,11 +599,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
-struct SitePlan {
-    bool ok;
-    int nk, nv, n_wo, wo_early;
-    uint32_t off_p, off_k, off_v, off_bar, a_stage_bytes, p_bytes, smem_bytes, wo_off[4];
-};
+}  // namespace
 
 SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs) {
     SitePlan p;
@@ -646,8 +642,6 @@ SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs) {
         }
     return p;
 }
-
-}  // namespace
 
 bool ipattn_site_supported(int C, int H, int Lt, int La) {
     const SiteGeom g = site_geom(C, H);

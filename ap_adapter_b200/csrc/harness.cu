@@ -268,9 +268,9 @@ static int case_site(int Bc, int S, int C, int H, int Lt, int La, int dt, bool c
         fails += compare("tcgen05 product vs simt", y_tc, y_simt, Bc * S, C, tol);
     }
     // each fused kernel on its own (the product path picks between them by grid size)
-    float t_var[3] = {0.f, 0.f, 0.f};
-    const char* vname[3] = {"", "all-heads site kernel", "one-head (cluster) site kernel"};
-    for (int v = 1; v <= 2 && fused; ++v) {
+    float t_var[4] = {0.f, 0.f, 0.f, 0.f};
+    const char* vname[4] = {"", "all-heads site kernel", "one-head (cluster) site kernel", "all-heads site kernel, 4 softmax warpgroups"};
+    for (int v = 1; v <= 3 && fused; ++v) {
         AK(apx_set_site_variant(v));
         if (apx_ipattn_site_kernel(Bc, S, C, H, Lt, La) == v) {
             CK(cudaMemset(Y[0], 0xFF, (size_t)Bc * S * C * 2));
@@ -286,8 +286,8 @@ static int case_site(int Bc, int S, int C, int H, int Lt, int La, int dt, bool c
     const float t_un = time_ms([&] { return run(APX_IMPL_TC_UNFUSED, 2, false); });
     const float t_simt = time_ms([&] { return run(APX_IMPL_SIMT, 1, false); }, 5);
     const double fl = 4.0 * Bc * S * (double)C * C + 4.0 * Bc * S * (double)L * C;
-    printf("  time per site call: product %.1f us (%.1f TFLOP/s, kernel choice %d)   all-heads %.1f us   one-head %.1f us   unfused %.1f us   simt %.1f us\n",
-           t_tc * 1e3, fl / t_tc * 1e-9, apx_ipattn_site_kernel(Bc, S, C, H, Lt, La), t_var[1] * 1e3, t_var[2] * 1e3, t_un * 1e3, t_simt * 1e3);
+    printf("  time per site call: product %.1f us (%.1f TFLOP/s, kernel choice %d)   all-heads %.1f us   all-heads/4wg %.1f us   one-head %.1f us   unfused %.1f us   simt %.1f us\n",
+           t_tc * 1e3, fl / t_tc * 1e-9, apx_ipattn_site_kernel(Bc, S, C, H, Lt, La), t_var[1] * 1e3, t_var[3] * 1e3, t_var[2] * 1e3, t_un * 1e3, t_simt * 1e3);
     AK(apx_set_impl(APX_IMPL_TC));
     return fails;
 }
@@ -340,6 +340,9 @@ int main(int argc, char** argv) {
     S("site_16x252x384_8+128_bf16", 16, 252, 384, 8, 8, 128, APX_BF16, false);
     S("site_16x64x640_8+512_f16", 16, 64, 640, 8, 8, 512, APX_F16, false);
     S("site_16x64x640_8+128_f16", 16, 64, 640, 8, 8, 128, APX_F16, false);
+    S("site_16x1000x256_8+120_bf16", 16, 1000, 256, 8, 8, 120, APX_BF16, false);
+    S("site_3x200x256_1+128_f16_cpu", 3, 200, 256, 8, 1, 128, APX_F16, true);
+    S("site_2x130x128_4h_16+113_f16_cpu", 2, 130, 128, 4, 16, 113, APX_F16, true);
     S("site_2x252x384_8+32_bf16", 2, 252, 384, 8, 8, 32, APX_BF16, false);
     S("site_2x64x640_8+8_f16", 2, 64, 640, 8, 8, 8, APX_F16, false);
     S("site_8x64x640_8+32_f16", 8, 64, 640, 8, 8, 32, APX_F16, false);

@@ -126,11 +126,13 @@ int apx_ipattn_pack(const void* Wq, const void* Wo, void* wpack, int C, int H, i
 /* 1 iff apx_ipattn_fwd runs this (C, H, context) as ONE fused kernel when given a pack */
 int apx_ipattn_fused_ok(int C, int H, int Lt, int La);
 /* Which kernel apx_ipattn_fwd picks for a call with a pack: 0 = three kernels, 1 = all-heads site kernel (one CTA per 128-query
- * tile: C <= 256), 2 = one-head-per-CTA site kernel (a cluster of H CTAs per tile: any C = H*d, H <= 8).  The choice between 1 and 2
- * follows the grid size; apx_set_site_variant pins it (measurements / tests): APX_SITE_AUTO, _ALLHEADS, _ONEHEAD. */
+ * tile: C <= 256), 2 = one-head-per-CTA site kernel (a cluster of H CTAs per tile: any C = H*d, H <= 8), 3 = the all-heads kernel with
+ * four softmax warpgroups (one tile per SM: batch >= ~5 clips at the S = 1000 sites, 16 + 128 padded context columns).  The choice
+ * follows the shape and the grid size; apx_set_site_variant pins it (measurements / tests): APX_SITE_AUTO, _ALLHEADS, _ONEHEAD. */
 #define APX_SITE_AUTO      0
 #define APX_SITE_ALLHEADS  1
 #define APX_SITE_ONEHEAD   2
+#define APX_SITE_ALLHEADS4 3   /* all-heads kernel with four softmax warpgroups (score rows split over two threads): full grids */
 int apx_ipattn_site_kernel(int Bc, int S, int C, int H, int Lt, int La);
 int apx_set_site_variant(int variant);
 

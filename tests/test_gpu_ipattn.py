@@ -108,6 +108,22 @@ def test_one_head_site_kernel_matches_oracle(name, dtype):
     assert ok, errs
 
 
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
+def test_four_warpgroup_site_kernel_matches_oracle(dtype):
+    """The opt-in all-heads variant with four softmax warpgroups (APX_SITE_ALLHEADS4; score rows split over two threads, audio maxima
+    exchanged through shared memory) on the S = 1000, C = 256 site with the shipped adapter weights."""
+    lib = _lib.load()
+    case = cases.make_ipattn_case("site256_real")
+    assert lib.apx_set_site_variant(_lib.APX_SITE_ALLHEADS4) == 0
+    try:
+        assert lib.apx_ipattn_site_kernel(2, 1000, 256, 8, 8, 128) == 3
+        y = run_site(case, dtype)
+        ok, errs = site_within_bar(y, case, dtype, "site_4wg/site256_real")
+    finally:
+        assert lib.apx_set_site_variant(_lib.APX_SITE_AUTO) == 0
+    assert ok, errs
+
+
 def test_tensor_core_and_cuda_core_paths_agree():
     lib = _lib.load()
     case = random_site_case(2, 300, 384, 8, 8, 128, seed=5)
