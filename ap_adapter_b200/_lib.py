@@ -43,6 +43,7 @@ SYMBOLS = {
     "apx_get_impl": (_I, []),
     "apx_launch_count": (c_uint64, []),
     "apx_linear": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "apx_linear_lnfold": (_I, [_P, _L, _P, _L, _P, _P, _F, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "apx_attention": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
     "apx_ctx_kv_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "apx_ctx_kv_workspace_bytes": (_Z, [_I, _I, _I, _I]),
@@ -200,6 +201,43 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, r
         check(lib.apx_linear(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(residual),
                              residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
                              dtype_code(a.dtype), dtype_code(out.dtype), epi, stream_ptr()), "apx_linear")
+    return out
+
+
+def fold_layernorm(w: torch.Tensor, bias: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor):
+    """(Wg, c1, c2) of apx_linear_lnfold for a projection ``w`` [N, K] (+ ``bias``) applied to LayerNorm(x; gamma, beta):
+    Wg = w * gamma in w's dtype, c1 = row sums of the ROUNDED Wg, c2 = w @ beta + bias (fp32)."""
+    with torch.no_grad():
+        wg = (w.float() * gamma.float()[None, :]).to(w.dtype).contiguous()
+        c1 = wg.float().sum(dim=1).contiguous()
+        c2 = w.float() @ beta.float()
+        if bias is not None:
+            c2 = c2 + bias.float()
+        return wg, c1, c2.contiguous()
+
+
+def linear_lnfold(a: torch.Tensor, wg: torch.Tensor, c1: torch.Tensor, c2: torch.Tensor, eps: float, residual: torch.Tensor | None = None,
+                  out_dtype: torch.dtype | None = None, gelu: bool = False, geglu: bool = False) -> torch.Tensor:
+    """act(LayerNorm(a) @ w^T + b) + residual with the LayerNorm folded into the GEMM (apx_linear_lnfold; see fold_layernorm)."""
+    lib = load()
+    dev = require_cuda(a, wg, c1, c2, residual)
+    assert a.dim() == 2 and wg.dim() == 2 and a.shape[1] == wg.shape[1] and a.dtype == wg.dtype and not (gelu and geglu)
+    a = a if a.stride(1) == 1 else a.contiguous()
+    m, k = a.shape
+    n = wg.shape[0]
+    out_dtype = out_dtype or a.dtype
+    out = torch.empty((m, n // 2 if geglu else n), dtype=out_dtype, device=dev)
+    epi = APX_EPI_GEGLU if geglu else APX_EPI_GELU if gelu else APX_EPI_NONE
+    assert c1.dtype == torch.float32 and c2.dtype == torch.float32 and c1.numel() == n and c2.numel() == n
+    if residual is not None:
+        assert residual.stride(1) == 1 and residual.shape == out.shape
+        if residual.dtype != torch.float32:
+            assert residual.dtype == out.dtype and out.dtype != torch.float32
+            epi |= APX_EPI_RES16
+    with torch.cuda.device(dev):
+        check(lib.apx_linear_lnfold(ptr(a), a.stride(0), ptr(wg), wg.stride(0), ptr(c1), ptr(c2), float(eps), ptr(residual),
+                                    residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
+                                    dtype_code(a.dtype), dtype_code(out.dtype), epi, stream_ptr()), "apx_linear_lnfold")
     return out
 
 

@@ -134,12 +134,25 @@ int apx_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const flo
     APX_REQUIRE(A && W && out, APX_EINVAL, "apx_linear: null pointer");
     APX_REQUIRE(out_dtype == APX_F16 || out_dtype == APX_BF16 || out_dtype == APX_F32, APX_EINVAL,
                 "apx_linear: out_dtype %d", out_dtype);
-    APX_REQUIRE((epilogue & ~7) == 0 && (epilogue & 3) != 3, APX_EINVAL, "apx_linear: epilogue %d", epilogue);
+    APX_REQUIRE((epilogue & ~7) == 0 && (epilogue & 3) != 3, APX_EINVAL, "apx_linear: epilogue %d (LayerNorm folding: apx_linear_lnfold)", epilogue);
     APX_REQUIRE((epilogue & 3) != APX_EPI_GEGLU || N % 32 == 0, APX_EUNSUPPORTED, "apx_linear: GEGLU needs N %% 32 == 0 (N=%d)", N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (current_impl() == APX_IMPL_SIMT)
         return gemm_simt(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue, st);
     return gemm_tc(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue, st);
+}
+
+int apx_linear_lnfold(const void* A, int64_t lda, const void* Wg, int64_t ldw, const float* c1, const float* c2, float eps,
+                      const float* residual, int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype,
+                      int epilogue, void* stream) {
+    APX_REQUIRE(A && Wg && c1 && c2 && out, APX_EINVAL, "apx_linear_lnfold: null pointer");
+    APX_REQUIRE(out_dtype == APX_F16 || out_dtype == APX_BF16 || out_dtype == APX_F32, APX_EINVAL, "apx_linear_lnfold: out_dtype %d", out_dtype);
+    APX_REQUIRE((epilogue & ~7) == 0 && (epilogue & 3) != 3, APX_EINVAL, "apx_linear_lnfold: epilogue %d", epilogue);
+    APX_REQUIRE((epilogue & 3) != APX_EPI_GEGLU || N % 32 == 0, APX_EUNSUPPORTED, "apx_linear_lnfold: GEGLU needs N %% 32 == 0 (N=%d)", N);
+    APX_REQUIRE(eps > 0.f, APX_EINVAL, "apx_linear_lnfold: eps %g", eps);
+    APX_REQUIRE(current_impl() != APX_IMPL_SIMT, APX_EUNSUPPORTED, "apx_linear_lnfold: tcgen05 path only");
+    return gemm_tc(A, lda, Wg, ldw, c2, residual, ldr, out, ldo, M, N, K, in_dtype, out_dtype, epilogue | APX_EPI_LNFOLD,
+                   static_cast<cudaStream_t>(stream), c1, eps);
 }
 
 int apx_attention(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V,

@@ -31,7 +31,7 @@ template <int BN>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_REGION = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGE_REGION + 256;   // + recv slabs when splits > 1
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGE_REGION + 256 + 1024;   // barriers | LayerNorm row statistics; + recv slabs when splits > 1
 };
 
 struct GemmArgs {
@@ -45,6 +45,8 @@ struct GemmArgs {
     int out_dtype;  // APX_F16 / APX_BF16 / APX_F32
     int epilogue;
     int splits;     // CTAs per cluster along K (1, 2, 4 or 8; > 1 only with BN = 64)
+    const float* ln_c1;   // APX_EPI_LNFOLD: c1[n] = sum_k W'[n, k] of the gamma-folded weight (bias then holds c2[n] = sum_k beta_k W[n, k] + b[n])
+    float ln_eps;
 };
 
 constexpr int LDP = 64 + 4;                        // fp32 row pitch of a staged 64-column tile in shared memory (words)
@@ -72,7 +74,13 @@ __device__ __forceinline__ Res8 load_res8(const GemmArgs& g, int row, int ocol, 
 
 // bias -> activation -> residual -> store for 8 consecutive accumulator columns of one row (col % 8 == 0)
 __device__ __forceinline__ void finish8(const GemmArgs& g, int row, int ocol, int nout, float (&v)[8], const float (&bias)[8],
-                                        const Res8& res) {
+                                        const Res8& res, const float (&c1)[8], float2 stat) {
+    if (g.epilogue & APX_EPI_LNFOLD) {
+        // LayerNorm folded into the GEMM: the accumulator is x · (W gamma)^T over the RAW rows; (x - mean) rstd comes out as
+        // rstd (acc - mean c1), and bias holds beta · W^T + b
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = stat.y * (v[i] - stat.x * c1[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += bias[i];
     const int epi = g.epilogue & 3;
@@ -123,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* recv_bar = acc_bar + 1;   // split-K: peers' partial slabs have landed in sRecv
     uint64_t* done_bar = acc_bar + 2;   // split-K: every peer has received everything (my outgoing copies are complete)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 3);
-    float* sRecv = reinterpret_cast<float*>(smem + GemmCfg<BN>::STAGE_REGION + 256);
+    float2* sStat = reinterpret_cast<float2*>(smem + GemmCfg<BN>::STAGE_REGION + 256);   // (mean, rstd) of the tile's 128 rows (APX_EPI_LNFOLD)
+    float* sRecv = reinterpret_cast<float*>(smem + GemmCfg<BN>::STAGE_REGION + 256 + 1024);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], (g.epilogue & APX_EPI_LNFOLD) ? 1 + 128 : 1);   // + the 128 statistics threads that read the A stage
         }
         mbar_init(acc_bar, 1);
         mbar_init(recv_bar, 1);
@@ -212,6 +221,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (g.bias) { b0 = *reinterpret_cast<const float4*>(g.bias + col); b1 = *reinterpret_cast<const float4*>(g.bias + col + 4); }
             bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
         }
+        float c1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g.epilogue & APX_EPI_LNFOLD) {
+            const float4 a0 = *reinterpret_cast<const float4*>(g.ln_c1 + col), a1 = *reinterpret_cast<const float4*>(g.ln_c1 + col + 4);
+            c1[0] = a0.x; c1[1] = a0.y; c1[2] = a0.z; c1[3] = a0.w; c1[4] = a1.x; c1[5] = a1.y; c1[6] = a1.z; c1[7] = a1.w;
+            // Row statistics of the A tile, read from the pipeline stages while the tensor core consumes them (one row per thread; the
+            // SWIZZLE_128B chunk order does not matter for sums).  Shifted by the row's first element against cancellation.
+            float shift = 0.f, s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&full_bar[s], (i / STAGES) & 1);
+                const uint4* rowp = reinterpret_cast<const uint4*>(sA + s * A_STAGE_BYTES + trow * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 w = rowp[j ^ (trow & 7)];   // chunk j of the row (SWIZZLE_128B: stored at j ^ (row & 7))
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float lo, hi;
+                        unpack16(ww[k], g.in_fmt, lo, hi);
+                        if (i == 0 && j == 0 && k == 0) shift = lo;
+                        lo -= shift; hi -= shift;
+                        s1 += lo + hi;
+                        s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                    }
+                }
+                mbar_arrive(&empty_bar[s]);
+            }
+            const float inv_k = 1.0f / static_cast<float>(g.K);
+            const float m = s1 * inv_k;
+            sStat[trow] = make_float2(shift + m, rsqrtf(fmaxf(s2 * inv_k - m * m, 0.f) + g.ln_eps));
+        }
         Res8 cur;
         cur.a = make_uint4(0, 0, 0, 0); cur.b = cur.a;
         if (g.residual && m0 + row_base + r0 < g.M) cur = load_res8(g, m0 + row_base + r0, ocol, nout);
@@ -265,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                     }
                 }
-                finish8(g, row, ocol, nout, v, bias, cur);
+                finish8(g, row, ocol, nout, v, bias, cur, c1, (g.epilogue & APX_EPI_LNFOLD) ? sStat[row_base + rl] : make_float2(0.f, 1.f));
             }
             cur = nxt;
         }
@@ -317,7 +357,7 @@ int pick_splits(int M, int N, int K) {
 
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
-            cudaStream_t st) {
+            cudaStream_t st, const float* ln_c1, float ln_eps) {
     APX_REQUIRE(in_dtype == APX_F16 || in_dtype == APX_BF16, APX_EUNSUPPORTED, "gemm_tc: in_dtype %d", in_dtype);
     APX_REQUIRE(K % BK == 0 && K > 0, APX_EUNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", K, BK);
     APX_REQUIRE(N % 64 == 0 && N > 0, APX_EUNSUPPORTED, "gemm_tc: N=%d must be a multiple of 64", N);
@@ -334,7 +374,10 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
 
     // Wide tiles once the grid already fills the machine, narrow ones otherwise; split-K clusters when even those leave SMs idle.
     const bool wide = (N % 128 == 0) && (static_cast<int64_t>(ceil_div(M, BM)) * (N / 128) >= 148);
-    const int splits = wide ? 1 : pick_splits(M, N, K);
+    APX_REQUIRE(!(epilogue & APX_EPI_LNFOLD) || (ln_c1 && bias && (reinterpret_cast<uintptr_t>(ln_c1) & 15) == 0), APX_EINVAL,
+                "gemm_tc: APX_EPI_LNFOLD needs c1 and c2 (16-byte aligned)");
+    // the row statistics of a folded LayerNorm are taken over the CTA's whole K range: no split-K
+    const int splits = (wide || (epilogue & APX_EPI_LNFOLD)) ? 1 : pick_splits(M, N, K);
     const int BN = wide ? 128 : 64;
 
     CUtensorMap tmA, tmB;
@@ -352,7 +395,7 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
         int rc = encode_tmap(&tmB, in_dtype, 2, W, dims, strides, box, 1);
         if (rc) return rc;
     }
-    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits};
+    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits, ln_c1, ln_eps};
     return wide ? launch_gemm<128>(tmA, tmB, g, st) : launch_gemm<64>(tmA, tmB, g, st);
 }
 

@@ -196,6 +196,31 @@ class FeedForward(nn.Module):
                 c = self._fused = (key, w, b, out.bias.float().contiguous(), src)
         return c[1:4]
 
+    # norm3 folded into the GEGLU GEMM (apx_linear_lnfold): one kernel less per block; APX_LN_FOLD=0 keeps the separate LayerNorm
+    fold_norm = os.environ.get("APX_LN_FOLD", "1") != "0"
+
+    def _packed_ln(self, norm: nn.LayerNorm):
+        """(Wg interleaved, c1, c2, fp32 out bias) for LayerNorm(norm) folded into the GEGLU projection."""
+        proj, out = self.net[0].proj, self.net[2]
+        src = (proj.weight, proj.bias, out.bias, norm.weight, norm.bias)
+
+        def build():
+            inner = proj.weight.shape[0] // 2
+            wg, c1, c2 = _lib.fold_layernorm(proj.weight.detach(), proj.bias.detach(), norm.weight.detach(), norm.bias.detach())
+            il = lambda t: torch.stack((t[:inner], t[inner:]), dim=1).reshape((2 * inner,) + t.shape[1:]).contiguous()  # noqa: E731
+            return il(wg), il(c1), il(c2), out.bias.detach().float().contiguous()
+
+        return _cached(self, "ln_fold", src, build)
+
+    def fused_ln(self, h, norm: nn.LayerNorm):
+        """ff(norm(h)) + h on (..., dim) 16-bit CUDA tensors, the LayerNorm folded into the first GEMM."""
+        wg, c1, c2, b2 = self._packed_ln(norm)
+        shape = h.shape
+        h2 = h.reshape(-1, shape[-1])
+        h2 = h2 if h2.stride(1) == 1 else h2.contiguous()
+        hidden = _lib.linear_lnfold(h2, wg, c1, c2, norm.eps, geglu=True)
+        return _lib.linear(hidden, self.net[2].weight, b2, residual=h2).reshape(shape)
+
     def fused(self, x, residual):
         """ff(x) + residual on (..., dim) 16-bit CUDA tensors."""
         w1, b1, b2 = self._packed()
@@ -249,6 +274,8 @@ class BasicTransformerBlock(nn.Module):
                                residual_inout=h.contiguous(), **kw)
             else:
                 h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask, **kw) + h
+        if self.ff.fold_norm and self.ff.fused_ok(h) and self.norm3.elementwise_affine:
+            return self.ff.fused_ln(h, self.norm3)
         x = self.norm3(h)
         if self.ff.fused_ok(x):
             return self.ff.fused(x, h)

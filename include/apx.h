@@ -61,6 +61,8 @@ extern "C" {
 #define APX_EPI_RES16     4   /* flag, OR-ed in: `residual` holds `out_dtype` (16-bit) elements instead of fp32; the GEMM value is
                                  rounded to `out_dtype` before the add, as a separate 16-bit `y + h` would                    */
 
+#define APX_EPI_LNFOLD    8   /* internal to apx_linear_lnfold: LayerNorm of the A rows folded into the GEMM                  */
+
 /* ---- kernel families ---------------------------------------------------------------- */
 #define APX_IMPL_TC           0   /* tcgen05 + TMA + TMEM (product path; single site kernel when packed weights are given) */
 #define APX_IMPL_SIMT         1   /* plain CUDA-core kernels: device-side cross-check for tests                     */
@@ -88,6 +90,21 @@ int apx_linear(const void* A, int64_t lda, const void* W, int64_t ldw,
                void* out, int64_t ldo,
                int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
                void* stream);
+
+/*
+ * Y = act( LayerNorm(A) · W^T + b ) [+ residual]  with the LayerNorm FOLDED into the GEMM (the `norm1` / `norm3` in front of the
+ * QKV / GEGLU projections of diffusers' BasicTransformerBlock, and timm Block's norm1 / norm2: one kernel instead of two, and the
+ * normalised activations never exist in memory):
+ *   Wg  = W * gamma[None, :]  (the caller folds the LayerNorm weight into the projection once per weight version), [N, K] `in_dtype`
+ *   c1  = fp32[N], c1[n] = sum_k Wg[n, k]                (of the ROUNDED Wg, so that a constant row normalises to exactly beta W^T + b)
+ *   c2  = fp32[N], c2[n] = sum_k beta[k] W[n, k] + b[n]
+ *   out = rstd_m (A · Wg^T - mean_m c1) + c2,  mean_m / rstd_m over the K elements of row m of A (biased variance, eps), computed
+ *         inside the kernel from the A tiles as they stream through shared memory.
+ * Same epilogue flags, dtypes and alignment rules as apx_linear; no split-K (a CTA must see whole rows).
+ */
+int apx_linear_lnfold(const void* A, int64_t lda, const void* Wg, int64_t ldw, const float* c1, const float* c2, float eps,
+                      const float* residual, int64_t ldr, void* out, int64_t ldo,
+                      int M, int N, int K, int in_dtype, int out_dtype, int epilogue, void* stream);
 
 /*
  * Segmented multi-head attention on token-major tensors.

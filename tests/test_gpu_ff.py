@@ -121,3 +121,49 @@ def test_plain_site_folds_to_out_and_residual_into_one_gemm(c, heads, s, cross):
     n0 = _lib.launch_count()
     got2 = attn(x, encoder_hidden_states=ctx, residual_inout=h)
     assert _lib.launch_count() == n0 and rel_err(got2, want) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("m,k,n,geglu,res", [(2000, 256, 2048, True, False), (504, 384, 3072, True, False), (128, 640, 5120, True, False),
+                                             (333, 256, 768, False, True), (1026, 768, 2304, False, False)],
+                         ids=["ff256", "ff384", "ff640", "qkv_res", "vit_qkv"])
+def test_linear_with_folded_layernorm_matches_torch(m, k, n, geglu, res, dtype):
+    """apx_linear_lnfold (LayerNorm of the A rows folded into the tcgen05 GEMM: statistics from the A tiles in shared memory, correction
+    in the epilogue) against LayerNorm -> Linear (-> GEGLU) in fp32 on the same 16-bit operands."""
+    import torch.nn.functional as F
+    from ap_adapter_b200 import _lib
+    from gpu_util import record, rel_err
+    g = torch.Generator().manual_seed(m + n)
+    x = (torch.randn(m, k, generator=g) * 1.5 + 0.8 * torch.randn(m, 1, generator=g) + 0.3).to(dtype)      # rows with their own offsets
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(dtype)
+    b = torch.randn(n, generator=g) * 0.2
+    gamma, beta = 1.0 + 0.3 * torch.randn(k, generator=g), 0.2 * torch.randn(k, generator=g)
+    r = torch.randn(m, n, generator=g).to(dtype) if res else None
+    ref = F.linear(F.layer_norm(x.float(), (k,), gamma, beta, 1e-5), w.float(), b)
+    if geglu:
+        ref = ref[:, 0::2] * F.gelu(ref[:, 1::2])
+    if res:
+        ref = ref + r.float()
+    wg, c1, c2 = _lib.fold_layernorm(w.cuda(), b.cuda(), gamma.cuda(), beta.cuda())
+    n0 = _lib.launch_count()
+    y = _lib.linear_lnfold(x.cuda(), wg, c1, c2, 1e-5, residual=r.cuda() if res else None, geglu=geglu)
+    assert _lib.launch_count() - n0 == 1
+    err = rel_err(y, ref)
+    record(f"linear_lnfold/{m}x{k}x{n}", dtype=str(dtype), err=err)
+    assert err < (2e-3 if dtype == torch.float16 else 1.2e-2)      # 16-bit rounding of W * gamma and of the output
+
+
+def test_feedforward_with_folded_norm_matches_separate_layernorm():
+    """FeedForward.fused_ln(h, norm3) == FeedForward.fused(norm3(h), h) up to the 16-bit rounding points."""
+    from ap_adapter_b200.unet import FeedForward
+    from gpu_util import rel_err
+    torch.manual_seed(3)
+    ff = FeedForward(384).cuda().half().eval()
+    norm = torch.nn.LayerNorm(384).cuda().half()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2); norm.bias.normal_(0.0, 0.2)
+        h = torch.randn(2, 252, 384, device="cuda", dtype=torch.float16)
+        a = ff.fused_ln(h, norm)
+        b = ff.fused(norm(h), h)
+        ref = ff.float()(torch.nn.functional.layer_norm(h.float(), (384,), norm.weight.float(), norm.bias.float(), norm.eps)) + h.float()
+    assert rel_err(a, ref) < 2e-3 and rel_err(b, ref) < 2e-3
