@@ -48,6 +48,10 @@ class AttnProcessor2_0(nn.Module):
     # inference on CUDA: prepared attention masks (and, with fuse_projections, the K / V of a cross-attention context) are cached per
     # tensor identity + version instead of being rebuilt at every site and step; False = rebuild every call, as the reference does
     cache_context = True
+    # inference on CUDA: the LayerNorm in front of the site (norm1 / norm2 of the transformer block) is folded into the Q(KV)
+    # projection (apx_linear_lnfold) when the block hands over the un-normalised stream (`fold_norm=`); only for sites with at
+    # least this many query rows (below that cuBLAS + a separate LayerNorm is as fast); APX_LN_FOLD_QKV=0 disables
+    fold_norm_min_rows = int(os.environ.get("APX_LN_FOLD_QKV", "1"))
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
@@ -64,13 +68,43 @@ class AttnProcessor2_0(nn.Module):
             c = self._cat = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous(), ws)
         return c[1]
 
-    def _project(self, attn, hidden_states, encoder_hidden_states, self_attention):
+    def can_fold_norm(self, attn, hidden_states, norm) -> bool:
+        """True when this call may take the un-normalised stream and fold `norm` into its first projection."""
+        n = self.fold_norm_min_rows
+        return (n > 0 and self.fuse_projections and hidden_states.is_cuda and not torch.is_grad_enabled() and hidden_states.dim() == 3
+                and hidden_states.dtype in (torch.float16, torch.bfloat16) and attn.to_q.weight.dtype == hidden_states.dtype
+                and attn.to_q.bias is None and attn.to_k.bias is None and attn.to_v.bias is None and norm.elementwise_affine
+                and hidden_states.shape[-1] % 64 == 0 and attn.to_q.out_features % 64 == 0
+                and hidden_states.shape[0] * hidden_states.shape[1] >= n
+                and attn.spatial_norm is None and attn.group_norm is None)
+
+    def _folded(self, mods, norm):
+        """(Wg, c1, c2) of the concatenated projection `mods` with `norm` folded in, cached per weight version."""
+        src = tuple(m.weight for m in mods) + (norm.weight, norm.bias)
+        key = tuple((w._version, w.data_ptr(), w.dtype) for w in src)
+        c = getattr(self, "_fold", None)
+        if c is None or c[0] != key or len(c[2]) != len(src) or any(a is not b for a, b in zip(c[2], src)):
+            w = torch.cat([m.weight.detach() for m in mods], dim=0)
+            c = self._fold = (key, _lib.fold_layernorm(w, None, norm.weight.detach(), norm.bias.detach()), src)
+        return c[1]
+
+    def _project(self, attn, hidden_states, encoder_hidden_states, self_attention, fold_norm=None):
         """(query, key, value) as (B, L, C) tensors (possibly strided views of one fused projection)."""
         fused = (self.fuse_projections and hidden_states.is_cuda and not torch.is_grad_enabled()
                  and attn.to_q.bias is None and attn.to_k.bias is None and attn.to_v.bias is None)
+        if fold_norm is not None:
+            # hidden_states is the UN-normalised stream: LayerNorm folded into the projection GEMM (one kernel instead of two)
+            b, s, c = hidden_states.shape
+            mods = (attn.to_q, attn.to_k, attn.to_v) if self_attention else (attn.to_q,)
+            wg, c1, c2 = self._folded(mods, fold_norm)
+            out = _lib.linear_lnfold(hidden_states.reshape(b * s, c), wg, c1, c2, fold_norm.eps).view(b, s, -1)
+            if self_attention:
+                return out.chunk(3, dim=-1)
+            hidden_states, query = None, out
         if fused and self_attention:
             return F.linear(hidden_states, self._cat_weight((attn.to_q, attn.to_k, attn.to_v))).chunk(3, dim=-1)
-        query = attn.to_q(hidden_states)
+        if fold_norm is None:
+            query = attn.to_q(hidden_states)
         if fused and encoder_hidden_states.dtype == attn.to_k.weight.dtype:
             # cross-attention context (T5 embeddings): K / V do not depend on the timestep — projected once per (context, weights)
             # identity + version and reused by every denoise step, like the adapter sites' context cache
@@ -82,7 +116,7 @@ class AttnProcessor2_0(nn.Module):
                 key, value = F.linear(encoder_hidden_states, self._cat_weight((attn.to_k, attn.to_v))).chunk(2, dim=-1)
                 c = self._kv = (ckey, key, value, encoder_hidden_states, ws)
             return query, c[1], c[2]
-        return query, attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)
+        return query, attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)   # (never reached with fold_norm: it requires `fused`)
 
     def _mask(self, attn, attention_mask, sequence_length, batch_size):
         """prepare_attention_mask + the per-head view (reference :245-249); cached per mask identity under inference: the T5
@@ -107,7 +141,9 @@ class AttnProcessor2_0(nn.Module):
             c = self._bo = (key, bo.detach().float().contiguous(), bo)
         return c[1]
 
-    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, residual_inout=None):
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, residual_inout=None,
+                 fold_norm=None):
+        """`fold_norm`: the block's LayerNorm, when `hidden_states` is the un-normalised stream (see can_fold_norm)."""
         residual = hidden_states
         if attn.spatial_norm is not None:
             hidden_states = attn.spatial_norm(hidden_states, temb)
@@ -129,7 +165,7 @@ class AttnProcessor2_0(nn.Module):
             encoder_hidden_states = hidden_states
         elif attn.norm_cross:
             encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
-        query, key, value = self._project(attn, hidden_states, encoder_hidden_states, self_attention)
+        query, key, value = self._project(attn, hidden_states, encoder_hidden_states, self_attention, fold_norm)
         head_dim = key.shape[-1] // attn.heads
         query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
         key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)

@@ -251,6 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float inv_k = 1.0f / static_cast<float>(g.K);
             const float m = s1 * inv_k;
             sStat[trow] = make_float2(shift + m, rsqrtf(fmaxf(s2 * inv_k - m * m, 0.f) + g.ln_eps));
+            // the accumulator tile is staged OVER the pipeline stages below: every statistics thread must be done reading them
+            named_bar_sync(1, 128);
         }
         Res8 cur;
         cur.a = make_uint4(0, 0, 0, 0); cur.b = cur.a;

@@ -259,21 +259,30 @@ class BasicTransformerBlock(nn.Module):
         # Inference on CUDA: processors that take `residual_inout` fold this block's residual add into their last kernel (the
         # adapter sites add into h in place — h is this block's own tensor by then —, the plain sites return a new tensor).
         fold = h.is_cuda and not torch.is_grad_enabled() and not h.requires_grad and self.fold_residual
-        x = self.norm1(h)
         ehs1 = encoder_hidden_states if self.only_cross_attention else None
-        if fold is True and getattr(self.attn1.processor, "accepts_residual", False):
-            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, residual_inout=h, **kw)
+        p1 = self.attn1.processor
+        kw1 = dict(kw)
+        if hasattr(p1, "can_fold_norm") and p1.can_fold_norm(self.attn1, h, self.norm1):
+            x, kw1["fold_norm"] = h, self.norm1          # norm1 runs inside the site's QKV projection
         else:
-            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, **kw) + h
+            x = self.norm1(h)
+        if fold is True and getattr(p1, "accepts_residual", False):
+            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, residual_inout=h, **kw1)
+        else:
+            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, **kw1) + h
         if self.attn2 is not None:
             # the adapter hot path: attn2's input is norm2(h), its output is residual-added right here
-            x = self.norm2(h)
-            if fold and getattr(self.attn2.processor, "accepts_residual", False) and (
-                    fold is True or getattr(self.attn2.processor, "folds_in_place", False)):
-                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask,
-                               residual_inout=h.contiguous(), **kw)
+            p2 = self.attn2.processor
+            kw2 = dict(kw)
+            if hasattr(p2, "can_fold_norm") and p2.can_fold_norm(self.attn2, h, self.norm2):
+                x, kw2["fold_norm"] = h, self.norm2      # plain (self / T5) attn2 sites: norm2 folded into the Q(KV) projection
             else:
-                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask, **kw) + h
+                x = self.norm2(h)
+            if fold and getattr(p2, "accepts_residual", False) and (fold is True or getattr(p2, "folds_in_place", False)):
+                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask,
+                               residual_inout=h.contiguous(), **kw2)
+            else:
+                h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask, **kw2) + h
         if self.ff.fold_norm and self.ff.fused_ok(h) and self.norm3.elementwise_affine:
             return self.ff.fused_ln(h, self.norm3)
         x = self.norm3(h)
