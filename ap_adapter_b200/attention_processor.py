@@ -50,8 +50,9 @@ class AttnProcessor2_0(nn.Module):
     cache_context = True
     # inference on CUDA: the LayerNorm in front of the site (norm1 / norm2 of the transformer block) is folded into the Q(KV)
     # projection (apx_linear_lnfold) when the block hands over the un-normalised stream (`fold_norm=`); only for sites with at
-    # least this many query rows (below that cuBLAS + a separate LayerNorm is as fast); APX_LN_FOLD_QKV=0 disables
-    fold_norm_min_rows = int(os.environ.get("APX_LN_FOLD_QKV", "1"))
+    # least this many query rows (measured on B200 at B = 1, ms per step: fold everywhere 10.34, >= 400 rows 10.44, >= 1000 rows 9.94,
+    # nowhere 10.11 — below ~1000 rows the unsplit tcgen05 GEMM loses to cuBLAS's split-K + a separate LayerNorm); APX_LN_FOLD_QKV=0 disables
+    fold_norm_min_rows = int(os.environ.get("APX_LN_FOLD_QKV", "1000"))
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()

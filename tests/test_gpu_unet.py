@@ -20,6 +20,13 @@ def _site_launches(bc=2, la=128) -> int:
     return sum(n * (1 if lib.apx_ipattn_site_kernel(bc, s, c, 8, 8, la) else 3) for n, s, c in ((10, 1000, 256), (10, 252, 384), (12, 64, 640)))
 
 
+def _folded_norm_sites(bc=2) -> int:
+    """Plain attention sites whose LayerNorm is folded into their Q(KV) projection (one extra libapx launch each): 14 plain sites per
+    attention-bearing resnet layer (8 attn1 + 6 non-adapter attn2), at the levels with at least fold_norm_min_rows query rows."""
+    n = AttnProcessor2_0.fold_norm_min_rows
+    return 0 if n <= 0 else sum(14 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if bc * s >= n)
+
+
 def _fused_ff_count(unet) -> int:
     with torch.no_grad():
         return sum(m.fused_ok(torch.empty(1, m.net[2].out_features, device="cuda", dtype=torch.float16))
@@ -66,7 +73,7 @@ def test_unet_step_matches_pytorch_processors(setup):
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values())
     assert n_ff == 128 and n_plain == 224
-    assert launched >= _site_launches() + 2 * n_ff + 109 + 22, launched     # + the channels-last route's GroupNorm / output-add kernels
+    assert launched >= _site_launches() + 2 * n_ff + 109 + 22 + _folded_norm_sites(), launched   # + channels-last GroupNorm / output adds, folded norms
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
     assert rel_err(y, y_ref) < 1e-2
@@ -88,7 +95,8 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     # residual GEMM is opt-in, APX_FOLD_RESIDUAL=1)
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values()) if BasicTransformerBlock.fold_residual is True else 0
-    assert per_step == _site_launches() + 2 * n_ff + n_plain + 109 + 22     # sites, FeedForwards, channels-last GroupNorms / output adds
+    # sites, FeedForwards, channels-last GroupNorms / output adds, Q(KV) projections with a folded LayerNorm
+    assert per_step == _site_launches() + 2 * n_ff + n_plain + 109 + 22 + _folded_norm_sites()
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)
