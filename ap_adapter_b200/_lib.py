@@ -58,6 +58,8 @@ SYMBOLS = {
     "apx_ipattn_fwd_add": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_ipattn_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "apx_ipattn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "apx_fbank_batch": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
+    "apx_resample": (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P]),
     "apx_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "apx_add_bias_nhwc": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "apx_audiomae_workspace_bytes": (_Z, [_I]),

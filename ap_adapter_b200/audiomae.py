@@ -269,37 +269,68 @@ def kaldi_mel_banks(num_bins: int = 128, padded_window: int = 512, sample_freq: 
     return torch.from_numpy(np.pad(bins, ((0, 0), (0, 1))).astype(np.float32))
 
 
+def sinc_resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """The windowed-sinc polyphase table of ``torchaudio.functional.resample`` (default ``sinc_interp_hann``; torchaudio is a third-party
+    dependency of the reference, AudioMAE.py:360-366): returns (taps fp32 [new, 2*width + orig], orig, new, width) with orig / new
+    reduced by their gcd.  taps[p, t] = sinc-Hann weight of input sample ``t - width`` for output phase ``p``."""
+    import math
+
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, :] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float64)[:, None] / new + idx
+    t = (t * base).clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    scale = base / orig
+    taps = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t) * window * scale
+    return taps.float().contiguous(), orig, new, width
+
+
 _MEL_FBT = {}
+_TAPS = {}
+
+
+def resample_to_16k(waveform: torch.Tensor, sampling_rate: int) -> torch.Tensor:
+    """(B, n) or (n,) CUDA waveform -> 16 kHz with libapx's polyphase resampler (apx_resample); same taps as torchaudio."""
+    if int(sampling_rate) == 16000:
+        return waveform
+    lib = _lib.load()
+    dev = waveform.device
+    w = waveform.reshape(-1, waveform.shape[-1]).float().contiguous()
+    key = (dev, int(sampling_rate))
+    if key not in _TAPS:
+        taps, orig, new, width = sinc_resample_taps(int(sampling_rate), 16000)
+        _TAPS[key] = (taps.to(dev), orig, new, width)
+    taps, orig, new, width = _TAPS[key]
+    b, n = w.shape
+    n_out = -(-new * n // orig)
+    out = torch.empty((b, n_out), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.apx_resample(_lib.ptr(w), b, n, _lib.ptr(taps), orig, new, width, _lib.ptr(out), _lib.stream_ptr()), "apx_resample")
+    return out.reshape(waveform.shape[:-1] + (n_out,))
 
 
 def extract_kaldi_fbank_feature(waveform, sampling_rate, log_mel_spec):
     """Reference ``AudioMAE.py:356-394``: resample to 16 kHz, remove DC, Kaldi fbank (128 mel bins, hanning, 10 ms
     shift), cut/pad to ``log_mel_spec.size(0)`` frames, normalise with the AudioSet statistics.
 
-    A CUDA waveform runs through ``apx_fbank`` (one hand-written kernel: framing, DC removal, pre-emphasis, window, 512-point
-    DFT, mel filterbank, log, normalisation); a CPU waveform takes the reference's own route (torchaudio's Kaldi fbank on
-    the host, which is where ``pipeline_audioldm2.py:919-925`` computes it)."""
+    A CUDA waveform runs through libapx: ``apx_resample`` (polyphase windowed-sinc, torchaudio's table) and ``apx_fbank`` (framing, DC
+    removal, pre-emphasis, window, 512-point DFT, mel filterbank, log, normalisation); a CPU waveform takes the reference's own route
+    (torchaudio on the host, which is where ``pipeline_audioldm2.py:919-925`` computes it)."""
     import torchaudio
 
     norm_mean = -4.2677393
     norm_std = 4.5689974
+    target_len = log_mel_spec.size(0)
+    if waveform.is_cuda:
+        return extract_kaldi_fbank_feature_batch(waveform.reshape(-1, waveform.shape[-1])[:1], sampling_rate, target_len)[0]  # channel 0
     if sampling_rate != 16000:
         waveform_16k = torchaudio.functional.resample(waveform, orig_freq=sampling_rate, new_freq=16000)
     else:
         waveform_16k = waveform
-    target_len = log_mel_spec.size(0)
-    if waveform_16k.is_cuda:
-        lib = _lib.load()
-        dev = waveform_16k.device
-        wav = waveform_16k.reshape(-1, waveform_16k.shape[-1])[0].float().contiguous()   # channel 0, as kaldi.fbank(channel=-1 -> 0)
-        if dev not in _MEL_FBT:
-            _MEL_FBT[dev] = kaldi_mel_banks().t().contiguous().to(dev)
-        out = torch.empty((target_len, 128), dtype=torch.float32, device=dev)
-        scratch = torch.empty(1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.apx_fbank(_lib.ptr(wav), wav.numel(), _lib.ptr(_MEL_FBT[dev]), _lib.ptr(out), target_len, _lib.ptr(scratch),
-                                     _lib.stream_ptr()), "apx_fbank")
-        return out
     waveform_16k = waveform_16k - waveform_16k.mean()
     fbank = torchaudio.compliance.kaldi.fbank(waveform_16k, htk_compat=True, sample_frequency=16000, use_energy=False,
                                               window_type="hanning", num_mel_bins=128, dither=0.0, frame_shift=10)
@@ -309,6 +340,25 @@ def extract_kaldi_fbank_feature(waveform, sampling_rate, log_mel_spec):
     elif p < 0:
         fbank = fbank[:target_len, :]
     return (fbank - norm_mean) / (norm_std * 2)
+
+
+def extract_kaldi_fbank_feature_batch(waveforms: torch.Tensor, sampling_rate: int, target_len: int = 1024) -> torch.Tensor:
+    """The same front-end for a BATCH of equally long mono clips on the GPU (the training collate, train_apadapter_v2.py:426-468, calls
+    the reference function clip by clip): (B, n) CUDA waveforms at ``sampling_rate`` -> (B, target_len, 128) normalised log-mel.
+    Two launches for the resampling-free case (per-clip means + one block per (frame, clip)), three otherwise."""
+    _lib.require_cuda(waveforms)
+    lib = _lib.load()
+    dev = waveforms.device
+    wav = resample_to_16k(waveforms.reshape(-1, waveforms.shape[-1]).float().contiguous(), sampling_rate)
+    b, n = wav.shape
+    if dev not in _MEL_FBT:
+        _MEL_FBT[dev] = kaldi_mel_banks().t().contiguous().to(dev)
+    out = torch.empty((b, target_len, 128), dtype=torch.float32, device=dev)
+    scratch = torch.empty(b, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.apx_fbank_batch(_lib.ptr(wav), b, n, _lib.ptr(_MEL_FBT[dev]), _lib.ptr(out), target_len, _lib.ptr(scratch),
+                                       _lib.stream_ptr()), "apx_fbank_batch")
+    return out
 
 
 def read_wav(path: str):

@@ -373,7 +373,15 @@ int apx_layernorm(const float* x, const float* w, const float* b, void* y, int r
 }
 int apx_fbank(const float* wave16k, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream) {
     APX_REQUIRE(wave16k && mel_fbT && out && scratch, APX_EINVAL, "apx_fbank: null pointer");
-    return fbank(wave16k, n_samples, mel_fbT, out, target_len, scratch, static_cast<cudaStream_t>(stream));
+    return fbank(wave16k, 1, n_samples, mel_fbT, out, target_len, scratch, static_cast<cudaStream_t>(stream));
+}
+int apx_fbank_batch(const float* wave16k, int B, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream) {
+    APX_REQUIRE(wave16k && mel_fbT && out && scratch, APX_EINVAL, "apx_fbank_batch: null pointer");
+    return fbank(wave16k, B, n_samples, mel_fbT, out, target_len, scratch, static_cast<cudaStream_t>(stream));
+}
+int apx_resample(const float* wave, int B, int n_samples, const float* taps, int orig, int new_, int width, float* out, void* stream) {
+    APX_REQUIRE(wave && taps && out, APX_EINVAL, "apx_resample: null pointer");
+    return resample(wave, B, n_samples, taps, orig, new_, width, out, static_cast<cudaStream_t>(stream));
 }
 int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_pool, void* stream) {
     APX_REQUIRE(xn && emb && B > 0, APX_EINVAL, "apx_pool_tokens: bad argument");

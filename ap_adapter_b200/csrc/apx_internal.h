@@ -118,7 +118,8 @@ int patch_embed(const float* mel, const float* pwT, const float* pb, const float
 int layernorm(const float* x, const float* w, const float* b, void* y, int rows, int cols, float eps, int out_dtype,
               cudaStream_t st);
 int pool_tokens(const float* xn, float* emb, int B, int tp, int fp, cudaStream_t st);
-int fbank(const float* wave16k, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st);
+int fbank(const float* wave16k, int B, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st);
+int resample(const float* x, int B, int n, const float* taps, int orig, int nw, int width, float* y, cudaStream_t st);
 
 int current_impl();
 

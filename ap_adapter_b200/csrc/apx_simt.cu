@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(192) pool_tokens_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wave_mean_kernel(const float* __restrict__ w, int n, float* __restrict__ mean) {
     __shared__ float red[8];
+    w += static_cast<size_t>(blockIdx.x) * n;      // one block per clip
+    mean += blockIdx.x;
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) s += w[i];
     s = warp_sum(s);
@@ -352,12 +354,14 @@ __global__ void __launch_bounds__(256) wave_mean_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wave, int n_frames, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wave, size_t wave_stride, int n_frames, const float* __restrict__ mean,
                                                    const float* __restrict__ melT /* [257][128] */, float* __restrict__ out,
                                                    float norm_mean, float norm_std2) {
     __shared__ float x[512], y[512], ct[512], st[512], pw[257 + 3], red[8];
     const int f = blockIdx.x, t = threadIdx.x;
-    float* orow = out + static_cast<size_t>(f) * 128;
+    wave += static_cast<size_t>(blockIdx.y) * wave_stride;                 // blockIdx.y = clip
+    mean += blockIdx.y;
+    float* orow = out + (static_cast<size_t>(blockIdx.y) * gridDim.x + f) * 128;
     if (f >= n_frames) {   // zero-padded frame
         if (t < 128) orow[t] = (0.f - norm_mean) / norm_std2;
         return;
@@ -474,14 +478,43 @@ int pool_tokens(const float* xn, float* emb, int B, int tp, int fp, cudaStream_t
     return APX_OK;
 }
 
-int fbank(const float* wave16k, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st) {
+int fbank(const float* wave16k, int B, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st) {
     APX_REQUIRE(n_samples >= 400, APX_EINVAL, "fbank: %d samples (one 25 ms frame needs 400)", n_samples);
-    APX_REQUIRE(target_len > 0, APX_EINVAL, "fbank: target_len=%d", target_len);
+    APX_REQUIRE(target_len > 0 && B > 0 && B <= 65535, APX_EINVAL, "fbank: target_len=%d B=%d", target_len, B);
     const int n_frames = 1 + (n_samples - 400) / 160;   // snip_edges
-    wave_mean_kernel<<<1, 256, 0, st>>>(wave16k, n_samples, scratch);
+    wave_mean_kernel<<<B, 256, 0, st>>>(wave16k, n_samples, scratch);
     APX_LAUNCH_CHECK("wave_mean_kernel");
-    fbank_kernel<<<target_len, 256, 0, st>>>(wave16k, std::min(n_frames, target_len), scratch, melT, out, -4.2677393f, 2.0f * 4.5689974f);
+    fbank_kernel<<<dim3(target_len, B), 256, 0, st>>>(wave16k, static_cast<size_t>(n_samples), std::min(n_frames, target_len), scratch, melT, out,
+                                                      -4.2677393f, 2.0f * 4.5689974f);
     APX_LAUNCH_CHECK("fbank_kernel");
+    return APX_OK;
+}
+
+// Polyphase FIR resampler (audio_encoder/AudioMAE.py:360-366 -> torchaudio.functional.resample, sinc interpolation with a Hann
+// window): with orig / new reduced by their gcd, output sample j * new + p of a clip is  sum_t taps[p][t] * x[j * orig + t - width]
+// (x zero outside the clip), for j * new + p < ceil(new * n / orig).  One thread per output sample, taps [new][kw] from L2.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, int n, const float* __restrict__ taps, int orig, int nw,
+                                                      int width, int kw, float* __restrict__ y, int n_out) {
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= n_out) return;
+    x += static_cast<size_t>(blockIdx.y) * n;
+    y += static_cast<size_t>(blockIdx.y) * n_out;
+    const int j = o / nw, p = o - j * nw;
+    const float* tp = taps + static_cast<size_t>(p) * kw;
+    const int i0 = j * orig - width;
+    const int t_lo = max(0, -i0), t_hi = min(kw, n - i0);
+    float acc = 0.f;
+    for (int t = t_lo; t < t_hi; ++t) acc = fmaf(tp[t], x[i0 + t], acc);
+    y[o] = acc;
+}
+
+int resample(const float* x, int B, int n, const float* taps, int orig, int nw, int width, float* y, cudaStream_t st) {
+    APX_REQUIRE(B > 0 && B <= 65535 && n > 0 && orig > 0 && nw > 0 && width >= 0, APX_EINVAL, "resample: bad argument");
+    const int kw = 2 * width + orig;
+    const long long n_out = (static_cast<long long>(nw) * n + orig - 1) / orig;
+    APX_REQUIRE(n_out > 0 && n_out < (1ll << 31), APX_EINVAL, "resample: output length %lld", n_out);
+    resample_kernel<<<dim3(static_cast<unsigned>((n_out + 255) / 256), B), 256, 0, st>>>(x, n, taps, orig, nw, width, kw, y, static_cast<int>(n_out));
+    APX_LAUNCH_CHECK("resample_kernel");
     return APX_OK;
 }
 

@@ -25,8 +25,9 @@
  *   apx_groupnorm_nhwc    nn.GroupNorm + F.silu (+ the conv-bias / time-embedding adds in front of it) inside diffusers' ResnetBlock2D /
  *   apx_add_bias_nhwc     Transformer2DModel as wired by pipeline/modeling_audioldm2.py:1047-1058,1223-1233,1399-1410 (third-party
  *                         leaves)
- *   apx_fbank             audio_encoder/AudioMAE.py:356-394 (extract_kaldi_fbank_feature; torchaudio's Kaldi fbank is a
+ *   apx_fbank(_batch)     audio_encoder/AudioMAE.py:356-394 (extract_kaldi_fbank_feature; torchaudio's Kaldi fbank is a
  *                         third-party dependency of the reference, restated from torchaudio 2.x compliance/kaldi.py)
+ *   apx_resample          audio_encoder/AudioMAE.py:360-366 (torchaudio.functional.resample to 16 kHz)
  *   apx_patch_embed       audio_encoder/models_mae.py:19-44 (PatchEmbed_org) + :552,561-563
  *   apx_layernorm         nn.LayerNorm(eps=1e-6) inside timm Block / models_mae.py:568
  *   apx_pool_tokens       audio_encoder/AudioMAE.py:148-182 (drop CLS, (avg+max)/2 pooling)
@@ -245,6 +246,16 @@ int apx_audiomae_encode(const float* mel, const apx_vit_weights* w_host, float* 
  *   transposed (host-built, ap_adapter_b200/audiomae.py::kaldi_mel_banks); out fp32[target_len, 128]; scratch >= 4 bytes.
  */
 int apx_fbank(const float* wave16k, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream);
+/* the same for a batch of equally long clips (the training collate, train_apadapter_v2.py:426-468): wave16k fp32[B, n_samples],
+ * out fp32[B, target_len, 128], scratch >= 4*B bytes */
+int apx_fbank_batch(const float* wave16k, int B, int n_samples, const float* mel_fbT, float* out, int target_len, float* scratch, void* stream);
+/*
+ * Resampling in front of the filterbank (audio_encoder/AudioMAE.py:360-366: torchaudio.functional.resample(waveform, sr, 16000);
+ * torchaudio's windowed-sinc polyphase resampler is a third-party dependency of the reference).  With orig / new the two rates
+ * divided by their gcd, `taps` fp32[new, 2*width + orig] the host-built windowed-sinc table (ap_adapter_b200/audiomae.py::sinc_resample_taps):
+ *   out[b, j*new + p] = sum_t taps[p, t] * wave[b, j*orig + t - width]   (wave = 0 outside [0, n_samples)),  out fp32[B, ceil(new*n_samples/orig)]
+ */
+int apx_resample(const float* wave, int B, int n_samples, const float* taps, int orig, int new_, int width, float* out, void* stream);
 
 /* individual stages (also used by the parity tests) */
 int apx_patch_embed(const float* mel, const float* patch_wT, const float* patch_b,

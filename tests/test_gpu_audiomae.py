@@ -139,7 +139,7 @@ def test_fbank_front_end_matches_torchaudio(sr, seconds):
     ref = extract_kaldi_fbank_feature(wav, sr, torch.zeros(1024, 128))                  # CPU: torchaudio
     n0 = _lib.launch_count()
     got = extract_kaldi_fbank_feature(wav.cuda(), sr, torch.zeros(1024, 128))           # CUDA: libapx
-    assert _lib.launch_count() - n0 == 2 and got.is_cuda and got.shape == (1024, 128)
+    assert _lib.launch_count() - n0 == 2 + (sr != 16000) and got.is_cuda and got.shape == (1024, 128)   # [resample,] per-clip mean, filterbank
     assert (got.cpu() - ref).abs().max().item() < 2e-3
 
 
@@ -155,3 +155,44 @@ def test_fbank_front_end_matches_reference_generated_golden():
     err = (got.cpu() - torch.from_numpy(gold)).abs().max().item()
     record("fbank/piano_vs_reference_golden", abs_err=err, bar=3e-3)
     assert got.shape == (1024, 128) and err < 3e-3
+
+
+def test_resample_kernel_matches_reference_generated_golden():
+    """apx_resample (polyphase windowed sinc, 48 kHz -> 16 kHz) on a 2 s excerpt of the reference's piano.wav against what the
+    reference's own route (torchaudio.functional.resample inside extract_kaldi_fbank_feature, AudioMAE.py:360-366) produced for it
+    (fixture written by oracle/gen_golden.py), plus 44.1 kHz / 22.05 kHz (160- and 320-phase tables) against torchaudio here."""
+    import torchaudio
+    from ap_adapter_b200.audiomae import resample_to_16k
+
+    f = np.load(os.path.join(cases.GOLDEN_DIR, "frontend_reference.npz"))
+    x48 = torch.from_numpy(f["piano48k_2s_i16"].astype(np.float32) / 32768.0)
+    got = resample_to_16k(x48.cuda(), 48000)
+    ref = torch.from_numpy(f["piano16k_2s"])
+    assert got.shape == ref.shape == (32000,)
+    err = (got.cpu() - ref).abs().max().item()
+    record("resample/piano_48k_vs_reference_golden", abs_err=err, bar=2e-5)
+    assert err < 2e-5                      # fp32 FIR sums, signal in [-1, 1]
+    g = torch.Generator().manual_seed(0)
+    for sr in (44100, 22050, 8000):
+        x = torch.randn(3, 30000, generator=g) * 0.3
+        y = resample_to_16k(x.cuda(), sr)
+        want = torchaudio.functional.resample(x, sr, 16000)
+        assert y.shape == want.shape and (y.cpu() - want).abs().max().item() < 5e-5
+
+
+def test_batched_front_end_equals_clip_by_clip():
+    """extract_kaldi_fbank_feature_batch (one launch set for B clips: the training collate, train_apadapter_v2.py:426-468) equals
+    the single-clip path bit for bit, and the reference-generated golden for the piano clip."""
+    from ap_adapter_b200.audiomae import extract_kaldi_fbank_feature, extract_kaldi_fbank_feature_batch
+
+    f = np.load(os.path.join(cases.GOLDEN_DIR, "frontend_reference.npz"))
+    piano = torch.from_numpy(f["piano16k"])
+    waves = torch.stack([piano, piano.flip(0) * 0.5 + 0.01, _synthetic_wave(16000, 10.0, 3)[0]]).cuda()
+    n0 = _lib.launch_count()
+    mel = extract_kaldi_fbank_feature_batch(waves, 16000, 1024)
+    assert _lib.launch_count() - n0 == 2 and mel.shape == (3, 1024, 128)
+    for i in range(3):
+        one = extract_kaldi_fbank_feature(waves[i:i + 1], 16000, torch.zeros(1024, 128))
+        assert torch.equal(one, mel[i])
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "audiomae_reference.npz"))["mel_piano_f16"].astype(np.float32)
+    assert (mel[0].cpu() - torch.from_numpy(gold)).abs().max().item() < 3e-3

@@ -353,3 +353,19 @@ def test_channels_last_route_is_the_same_function_as_the_stock_graph(tiny_unet, 
     assert y_nhwc.is_contiguous() and y_nhwc.shape == y_stock.shape
     assert ((y_nhwc - y_stock).abs().max() / y_stock.abs().max()).item() < 1e-5
     assert not U.NHWC.active and all("_temb_proj" not in r.__dict__ for r in tiny_unet._resnets())
+
+
+def test_sinc_resample_taps_match_torchaudio():
+    """The host-built polyphase table apx_resample consumes restates torchaudio's ``_get_sinc_resample_kernel`` (the third-party
+    routine behind the reference's resample call, AudioMAE.py:360-366)."""
+    import math
+
+    import torchaudio.functional as AF
+
+    from ap_adapter_b200.audiomae import sinc_resample_taps
+    for sr in (48000, 44100, 22050, 8000, 32000):
+        g = math.gcd(sr, 16000)
+        ref, width = AF.functional._get_sinc_resample_kernel(sr, 16000, g)
+        taps, orig, new, w = sinc_resample_taps(sr, 16000)
+        assert (orig, new, w) == (sr // g, 16000 // g, width) and taps.shape == ref[:, 0, :].shape
+        assert (taps - ref[:, 0, :]).abs().max().item() < 1e-5
