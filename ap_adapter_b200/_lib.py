@@ -26,7 +26,8 @@ _P, _I, _L, _F, _Z = c_void_p, c_int, c_int64, c_float, c_size_t
 
 class VitBlock(Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+        "qkv_wg", "qkv_c1", "qkv_c2", "fc1_wg", "fc1_c1", "fc1_c2")]   # ABI v3: LayerNorm-folded projections (None = separate LayerNorm)
 
 
 class VitWeights(Structure):

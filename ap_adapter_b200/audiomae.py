@@ -72,6 +72,9 @@ class MaskedAutoencoderViTEncoder(nn.Module):
     """Parameter container with the encoder half of ``mae_vit_base_patch16(in_chans=1, audio_exp=True,
     img_size=(1024,128))`` (``models_mae.py:689-701``); the forward is the fused kernel sequence."""
 
+    # norm1 / norm2 of every block folded into the qkv / fc1 GEMMs (24 fewer kernels per encode); APX_MAE_LN_FOLD=0 keeps them separate
+    fold_norms = __import__("os").environ.get("APX_MAE_LN_FOLD", "1") != "0"
+
     def __init__(self, depth: int = DEPTH):
         super().__init__()
         self.patch_embed = _PatchEmbed()
@@ -110,12 +113,19 @@ class MaskedAutoencoderViTEncoder(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
+        def folded(lin, norm):
+            # norm folded into lin (apx_linear_lnfold): Wg = W * gamma in the compute dtype, c1 = row sums of Wg, c2 = W beta + b
+            wg, c1, c2 = _lib.fold_layernorm(lin.weight.detach().to(cdt), lin.bias.detach(), norm.weight.detach(), norm.bias.detach())
+            keep.extend((wg, c1, c2))
+            return wg.data_ptr(), c1.data_ptr(), c2.data_ptr()
+
         blocks = (_lib.VitBlock * len(self.blocks))()
         for i, b in enumerate(self.blocks):
+            fold = (folded(b.attn.qkv, b.norm1) + folded(b.mlp.fc1, b.norm2)) if self.fold_norms else (None,) * 6
             blocks[i] = _lib.VitBlock(
                 f32(b.norm1.weight), f32(b.norm1.bias), w16(b.attn.qkv.weight), f32(b.attn.qkv.bias),
                 w16(b.attn.proj.weight), f32(b.attn.proj.bias), f32(b.norm2.weight), f32(b.norm2.bias),
-                w16(b.mlp.fc1.weight), f32(b.mlp.fc1.bias), w16(b.mlp.fc2.weight), f32(b.mlp.fc2.bias))
+                w16(b.mlp.fc1.weight), f32(b.mlp.fc1.bias), w16(b.mlp.fc2.weight), f32(b.mlp.fc2.bias), *fold)
         patch_wT = self.patch_embed.proj.weight.detach().float().reshape(EMBED, 256).t().contiguous()
         keep.append(patch_wT)
         w = _lib.VitWeights(len(self.blocks), EMBED, HEADS, MLP, _lib.dtype_code(cdt), patch_wT.data_ptr(),
@@ -124,21 +134,51 @@ class MaskedAutoencoderViTEncoder(nn.Module):
         self._pack = (key, (w, blocks, keep))
         return self._pack[1]
 
-    def encode_pooled(self, mel: torch.Tensor, time_pool: int, freq_pool: int) -> torch.Tensor:
-        """mel (B, 1024, 128) fp32 on the module's device -> (B, 512/(tp*fp), 768) fp32."""
+    # the ~80 launches of one encode are replayed from a CUDA graph (per batch size / pooling / weight version); APX_MAE_GRAPH=0 disables
+    use_graph = __import__("os").environ.get("APX_MAE_GRAPH", "1") != "0"
+
+    def _encode_pooled_eager(self, mel, emb, time_pool, freq_pool):
         lib = _lib.load()
         w, _, _ = self._weight_pack()
-        dev = self.cls_token.device
-        mel = mel.to(device=dev, dtype=torch.float32).contiguous()
+        dev = mel.device
         b = mel.shape[0]
-        ntok = (64 // time_pool) * (8 // freq_pool)
-        emb = torch.empty((b, ntok, EMBED), dtype=torch.float32, device=dev)
         wsb = lib.apx_audiomae_workspace_bytes(b)
         work = _lib.workspace(wsb, dev, "audiomae")
         with torch.cuda.device(dev):
             _lib.check(lib.apx_audiomae_fwd(_lib.ptr(mel), ctypes.byref(w), _lib.ptr(emb), b, int(time_pool), int(freq_pool),
                                             _lib.ptr(work), wsb, _lib.stream_ptr()), "apx_audiomae_fwd")
-        return emb
+
+    def encode_pooled(self, mel: torch.Tensor, time_pool: int, freq_pool: int) -> torch.Tensor:
+        """mel (B, 1024, 128) fp32 on the module's device -> (B, 512/(tp*fp), 768) fp32."""
+        dev = self.cls_token.device
+        if dev.type != "cuda":
+            raise _lib.ApxError("AudioMAE encoder weights are on the CPU; call .cuda() (no CPU fallback)")
+        mel = mel.to(device=dev, dtype=torch.float32).contiguous()
+        b = mel.shape[0]
+        ntok = (64 // time_pool) * (8 // freq_pool)
+        if not self.use_graph or torch.cuda.is_current_stream_capturing():
+            emb = torch.empty((b, ntok, EMBED), dtype=torch.float32, device=dev)
+            self._encode_pooled_eager(mel, emb, time_pool, freq_pool)
+            return emb
+        self._weight_pack()
+        key = (b, int(time_pool), int(freq_pool), self._pack[0])
+        g = self.__dict__.get("_graph")
+        if g is None or g["key"] != key:
+            g = dict(key=key, mel=torch.empty_like(mel), emb=torch.empty((b, ntok, EMBED), dtype=torch.float32, device=dev), ws={})
+            g["mel"].copy_(mel)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                      # warm-up off the capture (also validates the arguments)
+                self._encode_pooled_eager(g["mel"], g["emb"], time_pool, freq_pool)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with _lib.workspace_scope(g["ws"]), torch.cuda.graph(graph):
+                self._encode_pooled_eager(g["mel"], g["emb"], time_pool, freq_pool)
+            g["graph"] = graph
+            self.__dict__["_graph"] = g
+        g["mel"].copy_(mel)
+        g["graph"].replay()
+        return g["emb"].clone()
 
     def forward_encoder_no_random_mask_no_average(self, x: torch.Tensor) -> torch.Tensor:
         """(B,1,1024,128) -> (B,513,768), the un-pooled encoder output (``models_mae.py:548-570``)."""

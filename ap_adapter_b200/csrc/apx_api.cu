@@ -103,7 +103,7 @@ using namespace apx;
 extern "C" {
 
 const char* apx_last_error(void) { return g_err; }
-int apx_version(void) { return 2; }
+int apx_version(void) { return 3; }
 uint64_t apx_launch_count(void) { return g_launches.load(); }
 
 int apx_device_ok(void) {
@@ -389,7 +389,7 @@ int apx_pool_tokens(const float* xn, float* emb, int B, int time_pool, int freq_
 }
 
 struct MaeWorkspace {
-    size_t x, xn, qkv, att, hid, xf, tiles, total;
+    size_t x, xn, qkv, att, hid, xf, tiles, a16, res0, w16, total;
 };
 static MaeWorkspace mae_ws(int B) {
     const size_t rows = static_cast<size_t>(B) * 513;
@@ -402,6 +402,9 @@ static MaeWorkspace mae_ws(int B) {
     w.hid = off; off += align_up(rows * 3072 * 2, 256);
     w.xf = off;  off += align_up(rows * 768 * 4, 256);
     w.tiles = off; off += align_up(attention_tc_tiles_bytes(B, 12, 64, 513), 256);   // K / V^T operand tiles of one ViT block
+    w.a16 = off;  off += align_up(rows * 256 * 2, 256);    // patch matrix (A operand of the patch-embed GEMM)
+    w.res0 = off; off += align_up(rows * 768 * 4, 256);    // its fp32 residual operand (pos_embed / CLS rows)
+    w.w16 = off;  off += align_up(768 * 256 * 2, 256);     // conv weight as [768, 256] 16 bit
     w.total = off;
     return w;
 }
@@ -419,23 +422,50 @@ static int audiomae_encode_into(const float* mel, const apx_vit_weights* w, floa
     const float eps = 1e-6f;  // partial(nn.LayerNorm, eps=1e-6): audio_encoder/models_mae.py:698
     int rc;
 #define APX_STEP(call) do { rc = (call); if (rc) return rc; } while (0)
-    APX_STEP(apx_patch_embed(mel, w->patch_wT, w->patch_b, w->pos_embed, w->cls_token, x, B, stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool tc = current_impl() != APX_IMPL_SIMT;
+    const int fmt = dt == APX_F16 ? 0 : 1;
+    // xn doubles as the 16-bit copy of the residual stream (A operand of the GEMMs with a folded LayerNorm)
+    if (tc) {
+        // patch-embed on the tensor cores: patch matrix + residual table, then ONE GEMM with bias + fp32 residual epilogue
+        APX_STEP(patch_weight16(w->patch_wT, base + ws.w16, fmt, st));
+        APX_STEP(patchify(mel, w->pos_embed, w->cls_token, w->patch_b, base + ws.a16, reinterpret_cast<float*>(base + ws.res0), B, fmt, st));
+        APX_STEP(gemm_tc(base + ws.a16, 256, base + ws.w16, 256, w->patch_b, reinterpret_cast<const float*>(base + ws.res0), 768, x, 768, rows, 768,
+                         256, dt, APX_F32, APX_EPI_NONE, st, nullptr, 0.f, xn, 768));
+    } else {
+        APX_STEP(apx_patch_embed(mel, w->patch_wT, w->patch_b, w->pos_embed, w->cls_token, x, B, stream));
+    }
     for (int l = 0; l < w->depth; ++l) {
         const apx_vit_block& k = w->blocks[l];
+        const bool fold = tc && k.qkv_wg && k.qkv_c1 && k.qkv_c2 && k.fc1_wg && k.fc1_c1 && k.fc1_c2;
         // x += proj(attn(LN1(x)))
-        APX_STEP(apx_layernorm(x, k.ln1_w, k.ln1_b, xn, rows, 768, eps, dt, stream));
-        APX_STEP(apx_linear(xn, 768, k.qkv_w, 768, k.qkv_b, nullptr, 0, qkv, 2304, rows, 2304, 768, dt, dt, APX_EPI_NONE, stream));
-        if (current_impl() == APX_IMPL_SIMT)   // CUDA-core cross-check (shared-memory K/V, warp-shuffle softmax)
+        if (fold) {
+            APX_STEP(gemm_tc(xn, 768, k.qkv_wg, 768, k.qkv_c2, nullptr, 0, qkv, 2304, rows, 2304, 768, dt, dt, APX_EPI_LNFOLD, st, k.qkv_c1, eps));
+        } else {
+            APX_STEP(apx_layernorm(x, k.ln1_w, k.ln1_b, xn, rows, 768, eps, dt, stream));
+            APX_STEP(apx_linear(xn, 768, k.qkv_w, 768, k.qkv_b, nullptr, 0, qkv, 2304, rows, 2304, 768, dt, dt, APX_EPI_NONE, stream));
+        }
+        if (!tc)   // CUDA-core cross-check (shared-memory K/V, warp-shuffle softmax)
             APX_STEP(apx_attention(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304,
                                    att, 513LL * 768, 768, B, 513, 12, 64, 513, 513, 1.0f, 0.0f, dt, stream));
-        else                                   // product path: tcgen05 attention core, N = 513 keys in 128-column chunks
+        else       // product path: tcgen05 attention core, N = 513 keys in 128-column chunks
             APX_STEP(attention_tc(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304, att,
-                                  513LL * 768, 768, B, 513, 12, 64, 513, dt, base + ws.tiles, static_cast<cudaStream_t>(stream)));
-        APX_STEP(apx_linear(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, stream));
+                                  513LL * 768, 768, B, 513, 12, 64, 513, dt, base + ws.tiles, st));
+        if (tc) APX_STEP(gemm_tc(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, st, nullptr, 0.f,
+                                 fold ? xn : nullptr, 768));
+        else APX_STEP(apx_linear(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, stream));
         // x += fc2(GELU(fc1(LN2(x))))
-        APX_STEP(apx_layernorm(x, k.ln2_w, k.ln2_b, xn, rows, 768, eps, dt, stream));
-        APX_STEP(apx_linear(xn, 768, k.fc1_w, 768, k.fc1_b, nullptr, 0, hid, 3072, rows, 3072, 768, dt, dt, APX_EPI_GELU, stream));
-        APX_STEP(apx_linear(hid, 3072, k.fc2_w, 3072, k.fc2_b, x, 768, x, 768, rows, 768, 3072, dt, APX_F32, APX_EPI_NONE, stream));
+        if (fold) {
+            APX_STEP(gemm_tc(xn, 768, k.fc1_wg, 768, k.fc1_c2, nullptr, 0, hid, 3072, rows, 3072, 768, dt, dt, APX_EPI_GELU | APX_EPI_LNFOLD, st,
+                             k.fc1_c1, eps));
+        } else {
+            APX_STEP(apx_layernorm(x, k.ln2_w, k.ln2_b, xn, rows, 768, eps, dt, stream));
+            APX_STEP(apx_linear(xn, 768, k.fc1_w, 768, k.fc1_b, nullptr, 0, hid, 3072, rows, 3072, 768, dt, dt, APX_EPI_GELU, stream));
+        }
+        const bool next_fold = fold && l + 1 < w->depth;
+        if (tc) APX_STEP(gemm_tc(hid, 3072, k.fc2_w, 3072, k.fc2_b, x, 768, x, 768, rows, 768, 3072, dt, APX_F32, APX_EPI_NONE, st, nullptr, 0.f,
+                                 next_fold ? xn : nullptr, 768));
+        else APX_STEP(apx_linear(hid, 3072, k.fc2_w, 3072, k.fc2_b, x, 768, x, 768, rows, 768, 3072, dt, APX_F32, APX_EPI_NONE, stream));
     }
     APX_STEP(apx_layernorm(x, w->norm_w, w->norm_b, tokens, rows, 768, eps, APX_F32, stream));
 #undef APX_STEP

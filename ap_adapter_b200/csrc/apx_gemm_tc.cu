@@ -45,6 +45,8 @@ struct GemmArgs {
     int out_dtype;  // APX_F16 / APX_BF16 / APX_F32
     int epilogue;
     int splits;     // CTAs per cluster along K (1, 2, 4 or 8; > 1 only with BN = 64)
+    void* out2;           // optional second output [M, N]: the same values in the 16-bit INPUT format (row pitch ldo2 elements) — the
+    int64_t ldo2;         // A operand of the next GEMM when `out` is an fp32 residual stream
     const float* ln_c1;   // APX_EPI_LNFOLD: c1[n] = sum_k W'[n, k] of the gamma-folded weight (bias then holds c2[n] = sum_k beta_k W[n, k] + b[n])
     float ln_eps;
 };
@@ -105,6 +107,12 @@ __device__ __forceinline__ void finish8(const GemmArgs& g, int row, int ocol, in
             v[0] += __uint_as_float(res.a.x); v[1] += __uint_as_float(res.a.y); v[2] += __uint_as_float(res.a.z); v[3] += __uint_as_float(res.a.w);
             v[4] += __uint_as_float(res.b.x); v[5] += __uint_as_float(res.b.y); v[6] += __uint_as_float(res.b.z); v[7] += __uint_as_float(res.b.w);
         }
+    }
+    if (g.out2) {
+        uint16_t* op2 = reinterpret_cast<uint16_t*>(g.out2) + static_cast<int64_t>(row) * g.ldo2 + ocol;
+        const uint32_t q0 = pack16(v[0], v[1], g.in_fmt), q1 = pack16(v[2], v[3], g.in_fmt);
+        if (nout == 8) *reinterpret_cast<uint4*>(op2) = make_uint4(q0, q1, pack16(v[4], v[5], g.in_fmt), pack16(v[6], v[7], g.in_fmt));
+        else *reinterpret_cast<uint2*>(op2) = make_uint2(q0, q1);
     }
     if (g.out_dtype == APX_F32) {
         float* op = reinterpret_cast<float*>(g.out) + static_cast<int64_t>(row) * g.ldo + ocol;
@@ -359,7 +367,7 @@ int pick_splits(int M, int N, int K) {
 
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
-            cudaStream_t st, const float* ln_c1, float ln_eps) {
+            cudaStream_t st, const float* ln_c1, float ln_eps, void* out2, int64_t ldo2) {
     APX_REQUIRE(in_dtype == APX_F16 || in_dtype == APX_BF16, APX_EUNSUPPORTED, "gemm_tc: in_dtype %d", in_dtype);
     APX_REQUIRE(K % BK == 0 && K > 0, APX_EUNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", K, BK);
     APX_REQUIRE(N % 64 == 0 && N > 0, APX_EUNSUPPORTED, "gemm_tc: N=%d must be a multiple of 64", N);
@@ -397,7 +405,8 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
         int rc = encode_tmap(&tmB, in_dtype, 2, W, dims, strides, box, 1);
         if (rc) return rc;
     }
-    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits, ln_c1, ln_eps};
+    APX_REQUIRE(!out2 || (ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0), APX_EINVAL, "gemm_tc: out2 alignment");
+    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits, out2, ldo2, ln_c1, ln_eps};
     return wide ? launch_gemm<128>(tmA, tmB, g, st) : launch_gemm<64>(tmA, tmB, g, st);
 }
 

@@ -49,7 +49,7 @@ int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const ui
 // ---- tcgen05 kernels --------------------------------------------------------------------
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
-            cudaStream_t st, const float* ln_c1 = nullptr, float ln_eps = 0.f);
+            cudaStream_t st, const float* ln_c1 = nullptr, float ln_eps = 0.f, void* out2 = nullptr, int64_t ldo2 = 0);
 
 // Packed per-(batch, head) K / V^T tiles in UMMA no-swizzle K-major core-matrix order.
 // Per (batch, head) the cache holds three tiles: K, V^T, and V^T extended by 16 rows of which the first (row d_pad) is all ones
@@ -117,6 +117,10 @@ int patch_embed(const float* mel, const float* pwT, const float* pb, const float
                 int B, cudaStream_t st);
 int layernorm(const float* x, const float* w, const float* b, void* y, int rows, int cols, float eps, int out_dtype,
               cudaStream_t st);
+// patch-embed as a tensor-core GEMM: 16-bit patch matrix [B*513, 256] (row b*513 = zeros for CLS) + fp32 residual table [B*513, 768]
+// (pos_embed rows; cls + pos[0] - bias for the CLS row) + the conv weight as [768, 256] 16-bit
+int patchify(const float* mel, const float* pos, const float* cls, const float* pb, void* a16, float* res, int B, int fmt, cudaStream_t st);
+int patch_weight16(const float* pwT, void* w16, int fmt, cudaStream_t st);
 int pool_tokens(const float* xn, float* emb, int B, int tp, int fp, cudaStream_t st);
 int fbank(const float* wave16k, int B, int n_samples, const float* melT, float* out, int target_len, float* scratch, cudaStream_t st);
 int resample(const float* x, int B, int n, const float* taps, int orig, int nw, int width, float* y, cudaStream_t st);

@@ -256,6 +256,36 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     }
 }
 
+// Patch-embed as a GEMM (models_mae.py:19-44: Conv2d(1, 768, 16, stride 16) == [patches, 256] x [768, 256]^T): one block per
+// (clip, time step) turns its contiguous 16 x 128 mel strip into 8 patch rows of the 16-bit A operand (k = ky * 16 + kx, the order of
+// the flattened conv weight) and writes the matching rows of the fp32 residual operand (pos_embed; the CLS row carries cls + pos[0]
+// - bias behind an all-zero patch, so that the GEMM's bias epilogue leaves exactly cls + pos[0]).
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ mel, const float* __restrict__ pos, const float* __restrict__ cls,
+                                                      const float* __restrict__ pb, uint16_t* __restrict__ a16, float* __restrict__ res, int fmt) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    const float* src = mel + (static_cast<size_t>(b) * 1024 + t * 16) * 128;
+    const size_t row0 = static_cast<size_t>(b) * 513 + 1 + t * 8;
+    // strip element (ky, f * 16 + kx) -> A[row0 + f][ky * 16 + kx]; two adjacent kx per thread
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+        const int ky = i >> 6, c2 = (i & 63) * 2, f = c2 >> 4, kx = c2 & 15;
+        const float2 v = *reinterpret_cast<const float2*>(src + ky * 128 + c2);
+        *reinterpret_cast<uint32_t*>(a16 + (row0 + f) * 256 + ky * 16 + kx) = pack16(v.x, v.y, fmt);
+    }
+    for (int i = threadIdx.x; i < 8 * 768 / 4; i += 256)
+        reinterpret_cast<float4*>(res + row0 * 768)[i] = reinterpret_cast<const float4*>(pos + static_cast<size_t>(1 + t * 8) * 768)[i];
+    if (t == 0) {
+        const size_t r = static_cast<size_t>(b) * 513;
+        for (int e = threadIdx.x; e < 768; e += 256) res[r * 768 + e] = cls[e] + pos[e] - pb[e];
+        for (int e = threadIdx.x; e < 128; e += 256) reinterpret_cast<uint32_t*>(a16 + r * 256)[e] = 0u;
+    }
+}
+__global__ void __launch_bounds__(256) patch_weight16_kernel(const float* __restrict__ wT /* [256][768] */, uint16_t* __restrict__ w16 /* [768][256] */, int fmt) {
+    const int i = blockIdx.x * 256 + threadIdx.x;   // over 768 * 128 pairs
+    if (i >= 768 * 128) return;
+    const int n = i >> 7, k = (i & 127) * 2;
+    reinterpret_cast<uint32_t*>(w16)[i] = pack16(wT[static_cast<size_t>(k) * 768 + n], wT[static_cast<size_t>(k + 1) * 768 + n], fmt);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, two-pass statistics in registers, float4 I/O.  cols % 128 == 0, cols <= 1024.
 // ------------------------------------------------------------------------------------------------
@@ -457,6 +487,18 @@ int patch_embed(const float* mel, const float* pwT, const float* pb, const float
     APX_REQUIRE(B > 0, APX_EINVAL, "patch_embed: B=%d", B);
     patch_embed_kernel<<<dim3(64, B), 256, 0, st>>>(mel, pwT, pb, pos, cls, x);
     APX_LAUNCH_CHECK("patch_embed_kernel");
+    return APX_OK;
+}
+
+int patchify(const float* mel, const float* pos, const float* cls, const float* pb, void* a16, float* res, int B, int fmt, cudaStream_t st) {
+    APX_REQUIRE(B > 0 && B <= 65535, APX_EINVAL, "patchify: B=%d", B);
+    patchify_kernel<<<dim3(64, B), 256, 0, st>>>(mel, pos, cls, pb, static_cast<uint16_t*>(a16), res, fmt);
+    APX_LAUNCH_CHECK("patchify_kernel");
+    return APX_OK;
+}
+int patch_weight16(const float* pwT, void* w16, int fmt, cudaStream_t st) {
+    patch_weight16_kernel<<<768 * 128 / 256, 256, 0, st>>>(pwT, static_cast<uint16_t*>(w16), fmt);
+    APX_LAUNCH_CHECK("patch_weight16_kernel");
     return APX_OK;
 }
 

@@ -213,6 +213,10 @@ typedef struct apx_vit_block {
     const float* ln2_w; const float* ln2_b;
     const void*  fc1_w; const float* fc1_b;           /* [3072,768], fp32[3072]              */
     const void*  fc2_w; const float* fc2_b;           /* [768,3072], fp32[768]               */
+    /* optional (ABI v3): norm1 / norm2 folded into the qkv / fc1 GEMMs (see apx_linear_lnfold): Wg [N,768] wdtype, c1, c2 fp32[N].
+     * All six NULL = separate LayerNorm kernels. */
+    const void*  qkv_wg; const float* qkv_c1; const float* qkv_c2;
+    const void*  fc1_wg; const float* fc1_c1; const float* fc1_c2;
 } apx_vit_block;
 
 typedef struct apx_vit_weights {
