@@ -263,8 +263,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, l0:
 
 
 def groupnorm_nhwc_ok(hw: int, c: int, groups: int) -> bool:
-    """Shapes apx_groupnorm_nhwc takes (one group's HW x C/groups values are staged in shared memory as fp32)."""
-    return c % groups == 0 and (c // groups) % 4 == 0 and hw * (c // groups) * 4 <= 200 * 1024
+    """Shapes apx_groupnorm_nhwc takes (one group's HW x C/groups values are staged as fp32 in the shared memory of a cluster of up to
+    8 CTAs)."""
+    return c % groups == 0 and (c // groups) % 4 == 0 and hw * (c // groups) * 4 <= 8 * 190 * 1024
 
 
 def groupnorm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,

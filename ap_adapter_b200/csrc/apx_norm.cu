@@ -39,48 +39,81 @@ __device__ __forceinline__ float block_sum(float v, float* red) {   // blockDim.
     return t;
 }
 
-// One CTA per (group, batch element).  The group's HW x cpg values are staged ONCE in shared memory as fp32 (with the two adds
-// applied), so global memory is read once and written once; mean and variance are two exact passes over shared memory.
-__global__ void __launch_bounds__(512) groupnorm_nhwc_kernel(GnArgs a) {
-    extern __shared__ float sv[];           // [HW][cpg]
+// One CLUSTER of `cs` CTAs per (group, batch element); CTA r of the cluster owns the pixel slice [r * HW / cs, (r + 1) * HW / cs).
+// Its HW_r x cpg values are staged ONCE in shared memory as fp32 (with the two adds applied): global memory is read once and
+// written once.  Statistics: sum and sum of squares of (v - shift), shift = the group's first value (exact enough in fp32: the
+// shifted values are O(sigma)), block-reduced and exchanged between the CTAs of the cluster through distributed shared memory.
+// Loads are issued four at a time per thread: with one 8-byte load in flight a thread only sees the memory latency.
+__device__ __forceinline__ void gn_load4(const GnArgs& a, const uint16_t* xg, int b, int g, int q4, int item, float (&v)[4]) {
+    const int p = item / q4, q = item - p * q4;
+    const uint2 raw = *reinterpret_cast<const uint2*>(xg + static_cast<size_t>(p) * a.C + q * 4);
+    unpack16(raw.x, a.fmt, v[0], v[1]);
+    unpack16(raw.y, a.fmt, v[2], v[3]);
+    const int c = g * a.cpg + q * 4;
+    if (a.chan_bias) {
+        const float4 cb = *reinterpret_cast<const float4*>(a.chan_bias + c);
+        v[0] += cb.x; v[1] += cb.y; v[2] += cb.z; v[3] += cb.w;
+    }
+    if (a.bc_add) {
+        const uint2 t = *reinterpret_cast<const uint2*>(a.bc_add + static_cast<size_t>(b) * a.bc_stride + c);
+        float t0, t1, t2, t3;
+        unpack16(t.x, a.fmt, t0, t1);
+        unpack16(t.y, a.fmt, t2, t3);
+        v[0] += t0; v[1] += t1; v[2] += t2; v[3] += t3;
+    }
+}
+
+__global__ void __launch_bounds__(512) groupnorm_nhwc_kernel(GnArgs a, int cs) {
+    extern __shared__ float sv[];           // [HW_r][cpg]
     __shared__ float red[32];
-    const int g = blockIdx.x, b = blockIdx.y;
+    __shared__ float part[8][2];            // partial (sum, sum of squares) of every CTA of the cluster, written by their owners
+    const int g = blockIdx.x / cs, r = blockIdx.x - g * cs, b = blockIdx.y;
     const int q4 = a.cpg / 4;               // 4-channel (8-byte) pieces per pixel of this group
-    const int n4 = a.HW * q4;
-    const uint16_t* xg = a.x + static_cast<size_t>(b) * a.HW * a.C + g * a.cpg;
-    uint16_t* yg = a.y + static_cast<size_t>(b) * a.HW * a.C + g * a.cpg;
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const int p = i / q4, q = i - p * q4;
-        const uint2 raw = *reinterpret_cast<const uint2*>(xg + static_cast<size_t>(p) * a.C + q * 4);
-        float v[4];
-        unpack16(raw.x, a.fmt, v[0], v[1]);
-        unpack16(raw.y, a.fmt, v[2], v[3]);
-        const int c = g * a.cpg + q * 4;
-        if (a.chan_bias) {
-            const float4 cb = *reinterpret_cast<const float4*>(a.chan_bias + c);
-            v[0] += cb.x; v[1] += cb.y; v[2] += cb.z; v[3] += cb.w;
-        }
-        if (a.bc_add) {
-            const uint2 t = *reinterpret_cast<const uint2*>(a.bc_add + static_cast<size_t>(b) * a.bc_stride + c);
-            float t0, t1, t2, t3;
-            unpack16(t.x, a.fmt, t0, t1);
-            unpack16(t.y, a.fmt, t2, t3);
-            v[0] += t0; v[1] += t1; v[2] += t2; v[3] += t3;
-        }
-        *reinterpret_cast<float4*>(sv + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        sum += (v[0] + v[1]) + (v[2] + v[3]);
+    const int p_lo = static_cast<int>(static_cast<long long>(a.HW) * r / cs), p_hi = static_cast<int>(static_cast<long long>(a.HW) * (r + 1) / cs);
+    const int n4 = (p_hi - p_lo) * q4;
+    const uint16_t* xg = a.x + (static_cast<size_t>(b) * a.HW + p_lo) * a.C + g * a.cpg;
+    uint16_t* yg = a.y + (static_cast<size_t>(b) * a.HW + p_lo) * a.C + g * a.cpg;
+    float shift;
+    {   // the group's first value (pixel 0, first channel) with its adds: every CTA of the cluster computes the same number
+        float v0[4];
+        gn_load4(a, a.x + static_cast<size_t>(b) * a.HW * a.C + g * a.cpg, b, g, q4, 0, v0);
+        shift = v0[0];
     }
-    const float n = static_cast<float>(a.HW) * a.cpg;
-    const float mean = block_sum(sum, red) / n;
-    float sq = 0.f;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
-        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    float s1 = 0.f, s2 = 0.f;
+    const int step = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * step) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * step < n4) gn_load4(a, xg, b, g, q4, i0 + u * step, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * step < n4) {
+                *reinterpret_cast<float4*>(sv + (i0 + u * step) * 4) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = v[u][k] - shift;
+                    s1 += d;
+                    s2 = fmaf(d, d, s2);
+                }
+            }
     }
-    const float rstd = rsqrtf(block_sum(sq, red) / n + a.eps);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (cs > 1) {
+        if (threadIdx.x < cs) {             // thread t publishes this CTA's partials in CTA t's table
+            const uint32_t dst = map_to_cta(smem_u32(&part[r][0]), threadIdx.x);
+            asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(s1), "f"(s2) : "memory");
+        }
+        cluster_sync_all();
+        s1 = 0.f; s2 = 0.f;
+        for (int i = 0; i < cs; ++i) { s1 += part[i][0]; s2 += part[i][1]; }
+    }
+    const float inv_n = 1.0f / (static_cast<float>(a.HW) * a.cpg);
+    const float m = s1 * inv_n;
+    const float mean = shift + m;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_n - m * m, 0.f) + a.eps);
+    for (int i = threadIdx.x; i < n4; i += step) {
         const int p = i / q4, q = i - p * q4;
         const int c = g * a.cpg + q * 4;
         const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
@@ -137,8 +170,8 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: dtype %d", dtype);
     const int cpg = C / groups;
     APX_REQUIRE(cpg % 4 == 0, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: %d channels per group (need a multiple of 4)", cpg);
-    const size_t smem = static_cast<size_t>(HW) * cpg * 4;
-    APX_REQUIRE(smem <= 200 * 1024, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: a group of %d x %d values needs %zu B of shared memory", HW, cpg, smem);
+    APX_REQUIRE(static_cast<size_t>(HW) * cpg * 4 <= 8 * 190 * 1024, APX_EUNSUPPORTED,
+                "apx_groupnorm_nhwc: a group of %d x %d values does not fit the shared memory of a cluster of 8 CTAs", HW, cpg);
     APX_REQUIRE(B <= 65535, APX_EUNSUPPORTED, "apx_groupnorm_nhwc: B=%d", B);
     APX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(beta) & 15) == 0 && (reinterpret_cast<uintptr_t>(chan_bias) & 15) == 0 &&
@@ -149,9 +182,27 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
         APX_CUDA(cudaFuncSetAttribute(groupnorm_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     GnArgs a{static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), gamma, beta, chan_bias, static_cast<const uint16_t*>(bc_add), bc_stride,
              B, HW, C, groups, cpg, eps, silu ? 1 : 0, dtype == APX_F16 ? 0 : 1};
+    // a group is split over a cluster of 1 / 2 / 4 / 8 CTAs so that a CTA owns ~<= 2048 four-channel items (8 per thread at 256 threads):
+    // with one CTA per (group, clip) the B = 1 step ran 64 CTAs of up to 32 k values each, 26 us for the largest tensor
     const int n4 = HW * (cpg / 4);
-    const int threads = n4 >= 2048 ? 512 : n4 >= 512 ? 256 : 128;
-    groupnorm_nhwc_kernel<<<dim3(groups, B), threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    int cs = 1;
+    while (cs < 8 && (n4 / cs > 2048 || static_cast<size_t>(HW) * cpg * 4 / cs > 200 * 1024) && HW / (2 * cs) >= 1) cs *= 2;
+    const int per = (n4 + cs - 1) / cs;
+    const int threads = per >= 1024 ? 256 : per >= 256 ? 128 : 64;
+    const size_t smem = (static_cast<size_t>((HW + cs - 1) / cs) + 1) * cpg * 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * cs), B);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = static_cast<unsigned>(cs);
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    APX_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_nhwc_kernel, a, cs));
     APX_LAUNCH_CHECK("groupnorm_nhwc_kernel");
     return APX_OK;
 }

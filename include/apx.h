@@ -197,7 +197,7 @@ int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo
  *   x, y [B, HW, C] `dtype` (NHWC); gamma, beta fp32[C]; chan_bias fp32[C] or NULL (the bias of the convolution that produced x);
  *   bc_add [B, C] `dtype`, rows bc_stride elements apart, or NULL (ResnetBlock2D's time-embedding projection).  Statistics in fp32 over the SUMMED value, two
  *   exact passes; one rounding at the end.  Replaces conv-bias add + temb add + nn.GroupNorm (3 ATen kernels) + F.silu.
- *   Requires (C / groups) % 4 == 0 and HW * (C / groups) * 4 <= 200 KB (one group is staged in shared memory).
+ *   Requires (C / groups) % 4 == 0 and HW * (C / groups) * 4 <= 1600 KB (a group is staged in the shared memory of a cluster of <= 8 CTAs).
  */
 int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, const float* chan_bias, const void* bc_add, int64_t bc_stride,
                        void* y, int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream);

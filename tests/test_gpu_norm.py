@@ -21,6 +21,8 @@ pytestmark = pytest.mark.gpu
     ((2, 640, 32, 2), False, False),       # Transformer2DModel.norm (no SiLU)
     ((3, 1280, 32, 2), True, True),        # 40 channels per group (mid-level skip concat), odd batch
     ((16, 256, 125, 8), True, True),       # BASELINE batch 8
+    ((1, 256, 500, 16), True, True),       # a 20 s clip: 64 k values per group, a cluster of 8 CTAs
+    ((2, 128, 7, 3), False, True),         # fewer pixels than CTAs would like: no split
 ], ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
 def test_groupnorm_nhwc_matches_torch(shape, extras, silu, dtype):
     b, c, h, w = shape
@@ -47,7 +49,8 @@ def test_groupnorm_nhwc_matches_torch(shape, extras, silu, dtype):
 def test_groupnorm_rejects_what_it_does_not_cover():
     x = torch.zeros(1, 96, 4, 4, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
     w = torch.ones(96, device="cuda")
-    assert not _lib.groupnorm_nhwc_ok(16, 96, 32) and _lib.groupnorm_nhwc_ok(16, 128, 32) and not _lib.groupnorm_nhwc_ok(8000, 256, 32)
+    assert not _lib.groupnorm_nhwc_ok(16, 96, 32) and _lib.groupnorm_nhwc_ok(16, 128, 32) and _lib.groupnorm_nhwc_ok(8000, 256, 32)
+    assert not _lib.groupnorm_nhwc_ok(64000, 256, 32)
     with pytest.raises(_lib.ApxError, match="multiple of 4"):
         _lib.groupnorm_nhwc(x, w, w, 32, 1e-5, False)
 
