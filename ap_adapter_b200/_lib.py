@@ -57,6 +57,7 @@ SYMBOLS = {
     "apx_set_site_variant": (_I, [_I]),
     "apx_ipattn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_ipattn_fwd_add": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "apx_ipattn_fwd_ln": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P]),
     "apx_ipattn_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "apx_ipattn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "apx_fbank_batch": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),

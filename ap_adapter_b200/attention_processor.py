@@ -69,7 +69,7 @@ class AttnProcessor2_0(nn.Module):
             c = self._cat = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous(), ws)
         return c[1]
 
-    def can_fold_norm(self, attn, hidden_states, norm) -> bool:
+    def can_fold_norm(self, attn, hidden_states, norm, encoder_hidden_states=None) -> bool:
         """True when this call may take the un-normalised stream and fold `norm` into its first projection."""
         n = self.fold_norm_min_rows
         return (n > 0 and self.fuse_projections and hidden_states.is_cuda and not torch.is_grad_enabled() and hidden_states.dim() == 3
@@ -288,6 +288,7 @@ class IPAttnProcessor2_0(nn.Module):
     def invalidate_cache(self):
         self._ctx_cache = None
         self._w_cache = None
+        self._wln_cache = None
 
     def _site_weights(self, attn, heads: int, dtype: torch.dtype):
         """(to_q.weight, to_out[0].weight, packed blob) in the kernel dtype; the blob is the one-time re-layout the
@@ -342,12 +343,49 @@ class IPAttnProcessor2_0(nn.Module):
         self._ctx_cache = (key, cache, (ctx, wk, wv, wk_ip, wv_ip))
         return cache
 
+    # -- norm2 folded into the site kernel ----------------------------------------------------------------
+    fold_norm_enabled = os.environ.get("APX_LN_FOLD_SITE", "1") != "0"
+
+    def can_fold_norm(self, attn, hidden_states, norm, encoder_hidden_states=None) -> bool:
+        """True when this call can take the UN-normalised stream and run `norm` (the block's norm2) inside the site kernel
+        (apx_ipattn_fwd_ln): inference on CUDA in 16 bit at a shape the all-heads site kernel runs."""
+        if not (self.fold_norm_enabled and hidden_states.is_cuda and not torch.is_grad_enabled() and hidden_states.dim() == 3
+                and hidden_states.dtype in (torch.float16, torch.bfloat16) and norm.elementwise_affine
+                and encoder_hidden_states is not None and encoder_hidden_states.dim() == 3
+                and attn.spatial_norm is None and attn.group_norm is None and not attn.norm_cross
+                and getattr(attn.to_q, "bias", None) is None and hidden_states.shape[-1] == self.hidden_size):
+            return False
+        bc, s, c = hidden_states.shape
+        lt = min(self.num_tokens, encoder_hidden_states.shape[1])
+        la = encoder_hidden_states.shape[1] - lt
+        return _lib.load().apx_ipattn_site_kernel(bc, s, c, attn.heads, lt, la) == _lib.APX_SITE_ALLHEADS
+
+    def _site_weights_ln(self, attn, heads: int, dtype: torch.dtype, norm):
+        """(packed blob of (Wq * gamma, Wo), c1, c2) for norm folded into the q projection, cached per weight version."""
+        wq_p, wo_p = attn.to_q.weight, attn.to_out[0].weight
+        src = (wq_p, wo_p, norm.weight, norm.bias)
+        key = tuple(self._tkey(t) for t in src) + (heads, dtype)
+        c = getattr(self, "_wln_cache", None)
+        if c is not None and c[0] == key and all(a is b for a, b in zip(c[2], src)):
+            return c[1]
+        lib = _lib.load()
+        ch = self.hidden_size
+        wqg, c1, c2 = _lib.fold_layernorm(wq_p.detach().to(dtype), None, norm.weight.detach(), norm.bias.detach())
+        wo = wo_p.detach().to(dtype).contiguous()
+        pack = torch.empty(lib.apx_ipattn_pack_bytes(ch, heads), dtype=torch.uint8, device=wqg.device)
+        with torch.cuda.device(wqg.device):
+            _lib.check(lib.apx_ipattn_pack(_lib.ptr(wqg), _lib.ptr(wo), _lib.ptr(pack), ch, heads, _lib.dtype_code(dtype), _lib.stream_ptr()),
+                       "apx_ipattn_pack")
+        self._wln_cache = (key, (pack, c1, c2), src)
+        return self._wln_cache[1]
+
     # -- forward -----------------------------------------------------------------------------------------
     accepts_residual = True   # __call__ takes `residual_inout` (the restated transformer block passes its residual stream)
     folds_in_place = True     # ... and adds the site's output into it in place
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
-                 residual_inout=None):
+                 residual_inout=None, fold_norm=None):
+        """`fold_norm`: the block's norm2, when `hidden_states` is the un-normalised stream (only after can_fold_norm said yes)."""
         if scale != 1.0:
             warnings.warn("`scale` of IPAttnProcessor should be set by `set_ip_adapter_scale`.")
         if attention_mask is not None:
@@ -410,10 +448,27 @@ class IPAttnProcessor2_0(nn.Module):
                 hidden_states = hidden_states / attn.rescale_output_factor
             return hidden_states if residual_inout is None else hidden_states + residual_inout
         cache = self._context_cache(attn, encoder_hidden_states, heads, dtype)
-        wq, wo, wpack = self._site_weights(attn, heads, dtype)
         bo = attn.to_out[0].bias
         if bo is not None:
             bo = self._bias_f32(bo)
+        if fold_norm is not None:
+            # norm2 inside the site kernel: X is the raw stream, the pack holds Wq * gamma, the kernel takes the row statistics
+            pack, c1, c2 = self._site_weights_ln(attn, heads, dtype, fold_norm)
+            fold = (residual_inout is not None and input_ndim == 3 and not attn.residual_connection and attn.rescale_output_factor == 1.0
+                    and residual_inout.shape == x.shape and residual_inout.dtype == dtype and residual_inout.is_contiguous()
+                    and residual_inout.device == x.device and not (attn.to_out[1].training and attn.to_out[1].p > 0))
+            y = residual_inout if fold else torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.apx_ipattn_fwd_ln(_lib.ptr(x), _lib.ptr(cache), _lib.ptr(pack), _lib.ptr(bo), _lib.ptr(c1), _lib.ptr(c2),
+                                                 float(fold_norm.eps), _lib.ptr(y), bc, s, c, heads, lt, la, float(self.scale),
+                                                 _lib.dtype_code(dtype), 1 if fold else 0, _lib.stream_ptr()), "apx_ipattn_fwd_ln")
+            if fold:
+                return y
+            hidden_states = attn.to_out[1](y)
+            if attn.rescale_output_factor != 1.0:
+                hidden_states = hidden_states / attn.rescale_output_factor
+            return hidden_states if residual_inout is None else hidden_states + residual_inout
+        wq, wo, wpack = self._site_weights(attn, heads, dtype)
         wsb = lib.apx_ipattn_workspace_bytes(bc, s, c)
         work = _lib.workspace(wsb, x.device, "ipattn")
         # The block's residual add (h + attn2(norm2(h))) folded into the kernel: the site's output boxes are TMA-reduce-added

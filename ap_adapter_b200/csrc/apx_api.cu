@@ -296,7 +296,8 @@ int apx_ipattn_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
 
 static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, const void* Wo, const void* wpack, const float* bo,
                            void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, void* workspace,
-                           size_t workspace_bytes, void* stream, bool accumulate) {
+                           size_t workspace_bytes, void* stream, bool accumulate, const float* ln_c1 = nullptr, const float* ln_c2 = nullptr,
+                           float ln_eps = 0.f) {
     APX_REQUIRE(X && cache && Y, APX_EINVAL, "apx_ipattn_fwd: null pointer");
     APX_REQUIRE(Bc > 0 && S > 0 && C > 0 && H > 0 && C % H == 0 && Lt >= 0 && La >= 0 && Lt + La > 0, APX_EINVAL,
                 "apx_ipattn_fwd: bad shape Bc=%d S=%d C=%d H=%d Lt=%d La=%d", Bc, S, C, H, Lt, La);
@@ -308,9 +309,11 @@ static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, con
     if (current_impl() == APX_IMPL_TC && wpack) {
         const PackLayout pl = pack_layout(C, H);
         const int which = pick_site_kernel(Bc, S, C, H, Lt, La);
+        APX_REQUIRE(!ln_c1 || which == 1, APX_EUNSUPPORTED, "apx_ipattn_fwd_ln: only the all-heads site kernel folds the LayerNorm (kernel choice %d for "
+                    "Bc=%d S=%d C=%d H=%d context %d+%d; query apx_ipattn_site_kernel first)", which, Bc, S, C, H, Lt, La);
         if (which == 1)
             return ipattn_site(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt,
-                               La, ap_scale, dtype, accumulate, st);
+                               La, ap_scale, dtype, accumulate, st, ln_c1, ln_c2, ln_eps);
         if (which == 3)
             return ipattn_site4(X, static_cast<const uint8_t*>(wpack) + pl.site_off, cb + lay.tiles_off, bo, Y, Bc, S, C, H, Lt, La, ap_scale,
                                 dtype, accumulate, st);
@@ -319,6 +322,7 @@ static int ipattn_fwd_impl(const void* X, const void* Wq, const void* cache, con
                                   La, ap_scale, dtype, accumulate, st);
     }
 
+    APX_REQUIRE(!ln_c1, APX_EUNSUPPORTED, "apx_ipattn_fwd_ln: needs the packed weights and a shape the all-heads site kernel runs");
     APX_REQUIRE(Wq && Wo && workspace, APX_EINVAL, "apx_ipattn_fwd: the three-kernel path needs Wq, Wo and a workspace");
     APX_REQUIRE((C / H) % 8 == 0 && (C / H) <= 80, APX_EUNSUPPORTED,
                 "apx_ipattn_fwd: head dim %d (need d %% 8 == 0, d <= 80)", C / H);
@@ -356,6 +360,14 @@ int apx_ipattn_fwd_add(const void* X, const void* Wq, const void* cache, const v
                        size_t workspace_bytes, void* stream) {
     return ipattn_fwd_impl(X, Wq, cache, Wo, wpack, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, workspace, workspace_bytes, stream,
                            true);
+}
+
+int apx_ipattn_fwd_ln(const void* X, const void* cache, const void* wpack, const float* bo, const float* ln_c1, const float* ln_c2, float ln_eps,
+                      void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, int accumulate, void* stream) {
+    APX_REQUIRE(X && cache && wpack && ln_c1 && ln_c2 && Y, APX_EINVAL, "apx_ipattn_fwd_ln: null pointer");
+    APX_REQUIRE(ln_eps > 0.f, APX_EINVAL, "apx_ipattn_fwd_ln: eps %g", ln_eps);
+    return ipattn_fwd_impl(X, nullptr, cache, nullptr, wpack, bo, Y, Bc, S, C, H, Lt, La, ap_scale, dtype, nullptr, 0, stream, accumulate != 0,
+                           ln_c1, ln_c2, ln_eps);
 }
 
 // ---- AudioMAE -----------------------------------------------------------------------------------

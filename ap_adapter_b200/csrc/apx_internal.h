@@ -88,7 +88,8 @@ SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs);
 bool ipattn_site_supported(int C, int H, int Lt, int La);
 int ipattn_site_pack_weights(const void* Wq, const void* Wo, void* pack, int C, int H, int dtype, cudaStream_t st);
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
-                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
+                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st, const float* ln_c1 = nullptr,
+                const float* ln_c2 = nullptr, float ln_eps = 0.f);
 
 // ---- adapter site, one head per CTA + a cluster per query tile (apx_ipattn_h1.cu): any C = H * d with H <= 8 -------------------
 struct H1Geom {

@@ -117,6 +117,9 @@ struct SiteArgs {
     uint32_t off_p, off_k, off_v, off_bar;     // shared-memory offsets from the 1024-aligned base (sQO is at 0)
     uint32_t wo_off[4];                        // where each Wo stage lands
     int accumulate;                            // 1: Y += result (TMA reduce-add into the residual stream), 0: Y = result
+    const float* ln_c1;                        // norm2 folded into the q projection (null: X is already normalised): c1[n] = sum_k Wq'[n, k],
+    const float* ln_c2;                        // c2[n] = sum_k beta_k Wq[n, k]; the pack then holds Wq' = Wq * gamma
+    float ln_eps;
     long long* trace;                          // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0)
 };
 
@@ -128,9 +131,9 @@ struct SiteArgs {
 
 enum {  // mbarrier slots (40 x 8 bytes reserved; the TMEM slot and the bias slice follow)
     B_A_FULL = 0, B_K_FULL = 4, B_K_EMPTY = 7, B_V_FULL = 10, B_V_EMPTY = 13, B_WO_FULL = 16, B_Q = 20, B_SQ = 21, B_S_FULL = 22,
-    B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_OALL = 33, B_DONE = 34, B_COUNT = 35
+    B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_OALL = 33, B_DONE = 34, B_STAT = 35, B_COUNT = 36
 };
-constexpr uint32_t BAR_REGION_BYTES = 384;   // barriers [0, 320) | TMEM slot at 320 | bias slice from 384
+constexpr uint32_t BAR_REGION_BYTES = 384;   // barriers [0, 320) | TMEM slot at 320 | bias slice from 384 | folded-LayerNorm c1, c2 behind it
 
 // N16 > 0: the score row is N16 16-column groups, the first LT16 of them text, and it is read from tensor memory ONCE and kept
 //          in registers for both softmax passes (the score buffer is handed back to the MMA thread right after the load).
@@ -165,15 +168,24 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_prefetch_desc(&tmY);
 #pragma unroll 1
         for (int i = 0; i < B_COUNT; ++i) {
-            const uint32_t cnt = (i == B_SQ || i == B_SO_ALL) ? 256u : (i >= B_S_FREE && i < B_O_FULL) ? 128u
+            const uint32_t cnt = (i == B_SQ || i == B_SO_ALL || i == B_STAT) ? 256u : (i >= B_S_FREE && i < B_O_FULL) ? 128u
                                  : i == B_DONE ? static_cast<uint32_t>(a.cs > 1 ? a.cs - 1 : 1) : 1u;
             mbar_init(&bars[i], cnt);   // warpgroup -> MMA barriers count every arriving thread
         }
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc<512>(tmem_slot);
+    float* sLn = sBias + a.C;            // [2][Nq]: c1, c2 of the folded LayerNorm in the padded head layout
     if (threadIdx.x < 256) {
         for (int i = threadIdx.x; i < a.C; i += 256) sBias[i] = a.bo ? a.bo[i] : 0.f;
+        if (a.ln_c1) {
+            const int d = a.C / a.H;
+            for (int i = threadIdx.x; i < a.Nq; i += 256) {
+                const int hh = i / a.d_pad, j = i - hh * a.d_pad;
+                sLn[i] = j < d ? a.ln_c1[hh * d + j] : 0.f;
+                sLn[a.Nq + i] = j < d ? a.ln_c2[hh * d + j] : 0.f;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -204,7 +216,10 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             }
             // the K / V rings and the early Wo stages may be filled at once when the phase-A stages end below them (cluster
             // launches: small Wq slices); otherwise only when the Q accumulator is complete and the stages are dead
-            if (static_cast<uint32_t>(a.n_kb) * a.a_stage_bytes > a.off_k) mbar_wait_nocall(&bars[B_Q], 0);
+            if (static_cast<uint32_t>(a.n_kb) * a.a_stage_bytes > a.off_k) {
+                mbar_wait_nocall(&bars[B_Q], 0);
+                if (a.ln_c1) mbar_wait_nocall(&bars[B_STAT], 0);   // the warpgroups have finished reading the X chunks (row statistics)
+            }
             SITE_T(33);
             const uint8_t* kv_src = a.tiles + (static_cast<size_t>(b) * a.H + h_first) * a.kv_bytes;
             auto load_wo = [&](int w) {
@@ -383,6 +398,36 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int c_lo = g == 0 ? 0 : half, c_hi = g == 0 ? half : n16;
             const uint32_t dst0 = sQO_row + (h_first * a.d_pad / 8) * 2048;   // own heads' slot of sQO
             if (t0) SITE_T(tb + 120);
+            // norm2 folded into the q projection: mean / rstd of this thread's row from the X chunks in shared memory, while the
+            // tensor core multiplies them (both warpgroups, each for all 128 rows: no exchange); applied in the conversion below
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (a.ln_c1) {
+                float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait_nocall(&bars[B_A_FULL + kb], 0);
+                    const uint4* rowp = reinterpret_cast<const uint4*>(smem + kb * a.a_stage_bytes + row * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 w = rowp[j ^ (row & 7)];   // SWIZZLE_128B: chunk j of the row sits at j ^ (row & 7)
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float lo, hi;
+                            unpack16(ww[k], FMT, lo, hi);
+                            if (kb == 0 && j == 0 && k == 0) shift = lo;
+                            lo -= shift; hi -= shift;
+                            s1 += lo + hi;
+                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                        }
+                    }
+                }
+                const float inv = 1.0f / static_cast<float>(a.C), m = s1 * inv;
+                ln_mean = shift + m;
+                ln_rstd = rsqrtf(fmaxf(s2 * inv - m * m, 0.f) + a.ln_eps);
+                mbar_arrive(&bars[B_STAT]);
+                mbar_wait_nocall(&bars[B_STAT], 0);   // the Q tile below is written OVER the phase-A stages: every row must have been read
+            }
             mbar_wait_nocall(&bars[B_Q], 0);
             tc_fence_after();
             if (a.cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // phase-A stages are dead here
@@ -396,7 +441,19 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (c0 + j < c_hi) { reg_tie16(r + j * 16); cvt_store16<FMT>(r + j * 16, dst0 + (c0 + j) * 2 * 2048); }
+                    if (c0 + j < c_hi) {
+                        reg_tie16(r + j * 16);
+                        if (a.ln_c1) {   // q = rstd (x Wq'^T - mean c1) + c2
+                            const float* c1p = sLn + (h_first * a.d_pad) + (c0 + j) * 16;
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                v[i] = fmaf(ln_rstd, __uint_as_float(r[j * 16 + i]) - ln_mean * c1p[i], c1p[a.Nq + i]);
+                            store16<FMT>(dst0 + (c0 + j) * 2 * 2048, v);
+                        } else {
+                            cvt_store16<FMT>(r + j * 16, dst0 + (c0 + j) * 2 * 2048);
+                        }
+                    }
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -634,7 +691,7 @@ SitePlan site_plan(const SiteGeom& g, int Lt, int La, int cs) {
             off = std::max(off, static_cast<uint32_t>(g.n_kb) * p.a_stage_bytes);   // the phase-A stages overlay all of the above
             off = std::max(off, p.off_p + static_cast<uint32_t>(g.C / cs / 64) * X_CHUNK_BYTES);   // and so do the Y staging boxes
             p.off_bar = static_cast<uint32_t>(align_up(off, 128));
-            const uint32_t total = p.off_bar + BAR_REGION_BYTES + static_cast<uint32_t>(g.C) * 4;
+            const uint32_t total = p.off_bar + BAR_REGION_BYTES + static_cast<uint32_t>(g.C) * 4 + static_cast<uint32_t>(g.Nq) * 8;   // bias | c1, c2
             if (total <= limit) {
                 p.ok = true; p.nk = ring; p.nv = ring; p.wo_early = early; p.smem_bytes = total + 1024;
                 return p;
@@ -672,7 +729,8 @@ int ipattn_site_pick_cluster(int Bc, int S, int C, int H) {
 }
 
 int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C,
-                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st) {
+                int H, int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st, const float* ln_c1, const float* ln_c2,
+                float ln_eps) {
     APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "ipattn_site: dtype %d", dtype);
     int cs = ipattn_site_pick_cluster(Bc, S, C, H);
     const SiteGeom g = site_geom(C, H);
@@ -708,6 +766,8 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
     a.Lt = Lt; a.La = La; a.Lt_pad = kg.Lt_pad; a.La_pad = kg.La_pad; a.L_pad = kg.L_pad;
     a.ap_scale = ap_scale;
     a.accumulate = accumulate ? 1 : 0;
+    APX_REQUIRE((ln_c1 == nullptr) == (ln_c2 == nullptr), APX_EINVAL, "ipattn_site: c1 and c2 of the folded LayerNorm come together");
+    a.ln_c1 = ln_c1; a.ln_c2 = ln_c2; a.ln_eps = ln_eps;
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(g.d));
     a.kv_bytes = static_cast<uint32_t>(kg.bytes_per_bh);
     a.k_tile_bytes = static_cast<uint32_t>(kg.k_tile_bytes);

@@ -435,7 +435,7 @@ bool ipattn_site4_supported(int C, int H, int Lt, int La) {
     if (kg.Lt_pad != LT_PAD || kg.La_pad != LA_PAD) return false;
     if (2 * L_PAD + 4 * kg.dv_pad > 512) return false;
     const SitePlan p = site_plan(g, Lt, La, 1);
-    return p.ok && p.smem_bytes - (384 + static_cast<uint32_t>(C) * 4) + TAIL_BYTES <= 227u * 1024u;
+    return p.ok && p.off_bar + TAIL_BYTES + 1024 <= 227u * 1024u;
 }
 
 int ipattn_site4(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C, int H,

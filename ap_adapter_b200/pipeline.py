@@ -215,9 +215,9 @@ class APAdapterDenoiser(nn.Module):
     def _site_blobs(self):
         out = []
         for proc in self._adapter_procs():
-            ctx_c, w_c = getattr(proc, "_ctx_cache", None), getattr(proc, "_w_cache", None)   # libapx processors only
-            out.append(None if ctx_c is None else ctx_c[1])
-            out.append(None if w_c is None else w_c[1])
+            for name in ("_ctx_cache", "_w_cache", "_wln_cache"):                              # libapx processors only
+                c = getattr(proc, name, None)
+                out.append(None if c is None else c[1])
         return out
 
     # ---- end to end (pipeline_audioldm2.py:748-1034, minus text encoders / VAE / vocoder) -------------------------------

@@ -274,8 +274,8 @@ class BasicTransformerBlock(nn.Module):
             # the adapter hot path: attn2's input is norm2(h), its output is residual-added right here
             p2 = self.attn2.processor
             kw2 = dict(kw)
-            if hasattr(p2, "can_fold_norm") and p2.can_fold_norm(self.attn2, h, self.norm2):
-                x, kw2["fold_norm"] = h, self.norm2      # plain (self / T5) attn2 sites: norm2 folded into the Q(KV) projection
+            if hasattr(p2, "can_fold_norm") and p2.can_fold_norm(self.attn2, h, self.norm2, encoder_hidden_states):
+                x, kw2["fold_norm"] = h, self.norm2      # norm2 folded into the adapter site kernel / a plain site's Q(KV) projection
             else:
                 x = self.norm2(h)
             if fold and getattr(p2, "accepts_residual", False) and (fold is True or getattr(p2, "folds_in_place", False)):

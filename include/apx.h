@@ -179,6 +179,17 @@ int apx_ipattn_fwd_add(const void* X, const void* Wq, const void* cache, const v
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same site with the transformer block's `norm2` LayerNorm folded into the kernel (diffusers BasicTransformerBlock:
+ * `attn2(norm2(h), ctx) + h`, the call sites pipeline/modeling_audioldm2.py:1140-1156, 1317-1333, 1492-1508):
+ *   X = the UN-normalised stream h; `wpack` = apx_ipattn_pack of (Wq * gamma[None, :], Wo); ln_c1[n] = sum_k (Wq*gamma)[n, k] (of the rounded
+ *   product), ln_c2[n] = sum_k beta[k] Wq[n, k], both fp32[C]; q = rstd (x Wq'^T - mean c1) + c2 with the row statistics taken inside the
+ *   kernel from the X tiles it has staged for the projection.  accumulate != 0: Y <- Y + site (Y may alias X: the block's residual stream).
+ * Only the all-heads site kernel folds the norm: call it when apx_ipattn_site_kernel(...) == APX_SITE_ALLHEADS, else APX_EUNSUPPORTED.
+ */
+int apx_ipattn_fwd_ln(const void* X, const void* cache, const void* wpack, const float* bo, const float* ln_c1, const float* ln_c2, float ln_eps,
+                      void* Y, int Bc, int S, int C, int H, int Lt, int La, float ap_scale, int dtype, int accumulate, void* stream);
+
+/*
  * Backward of one adapter site for adapter-only training (train_apadapter_v2.py:892-979: only to_k_ip / to_v_ip train, the
  * UNet is frozen, and the loss must still reach the adapter sites further up, hence dX):
  *   dY, X, dX [Bc, S, C] `dtype`; Wq, Wo [C, C] `dtype` (as in apx_ipattn_fwd); `cache` = the context cache the forward used

@@ -124,6 +124,45 @@ def test_four_warpgroup_site_kernel_matches_oracle(dtype):
     assert ok, errs
 
 
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 1000, 256, 8, 8, 128), (16, 1000, 256, 8, 8, 128), (3, 129, 256, 8, 8, 24), (2, 200, 128, 4, 8, 32)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_site_with_folded_norm2_matches_oracle(shape, dtype):
+    """apx_ipattn_fwd_ln: the block's norm2 LayerNorm inside the all-heads site kernel (row statistics from the staged X tiles, Wq *
+    gamma in the pack, correction in the Q conversion) against LayerNorm -> oracle site in fp32 on the same 16-bit operands, with and
+    without the residual folded in (Y aliasing X)."""
+    bc, s, c, h, lt, la = shape
+    case = random_site_case(bc, s, c, h, lt, la, scale=0.6, seed=sum(shape))
+    g = torch.Generator().manual_seed(1)
+    case["x"] = case["x"] * 1.7 + 0.6 * torch.randn(bc, s, 1, generator=g) + 0.25           # rows with their own offset and scale
+    norm = torch.nn.LayerNorm(c)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.25, generator=g); norm.bias.normal_(0.0, 0.2, generator=g)
+    attn, proc = build_site(case, dtype)
+    norm_d = norm.to("cuda", dtype)
+    x = case["x"].to("cuda", dtype)
+    ctx = case["ctx"].to("cuda", dtype)
+    assert proc.can_fold_norm(attn, x, norm_d, ctx)
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        y = proc(attn, x, encoder_hidden_states=ctx, fold_norm=norm_d)
+        built = _lib.launch_count() - n0
+        n0 = _lib.launch_count()
+        h_res = x.clone()
+        y2 = proc(attn, x, encoder_hidden_states=ctx, fold_norm=norm_d, residual_inout=h_res)      # h + site(norm2(h)), in place
+        assert _lib.launch_count() - n0 == 1 and built >= 1 and y2.data_ptr() == h_res.data_ptr()
+        h_alias = x.clone()
+        y3 = proc(attn, h_alias, encoder_hidden_states=ctx, fold_norm=norm_d, residual_inout=h_alias)  # X and Y are the same buffer
+    xr = case["x"].to(dtype).float()
+    xn = torch.nn.functional.layer_norm(xr, (c,), norm.weight.to(dtype).float(), norm.bias.to(dtype).float(), norm.eps)
+    ref = oracle_site(dict(case, x=xn), dtype)          # oracle_site rounds x again: the reference's LayerNorm output is 16-bit too
+    err = rel_err(y, ref)
+    record("site_ln/" + "x".join(map(str, shape)), dtype=str(dtype), err=err)
+    assert err < (1.5e-3 if dtype == torch.float16 else 1e-2)
+    assert torch.equal(y2, (y.float() + x.float()).to(dtype)) or rel_err(y2, ref + xr) < (1.5e-3 if dtype == torch.float16 else 1e-2)
+    assert torch.equal(y3, y2)
+
+
 def test_tensor_core_and_cuda_core_paths_agree():
     lib = _lib.load()
     case = random_site_case(2, 300, 384, 8, 8, 128, seed=5)

@@ -24,7 +24,7 @@ def _folded_norm_sites(bc=2) -> int:
     """Plain attention sites whose LayerNorm is folded into their Q(KV) projection (one extra libapx launch each): 14 plain sites per
     attention-bearing resnet layer (8 attn1 + 6 non-adapter attn2), at the levels with at least fold_norm_min_rows query rows."""
     n = AttnProcessor2_0.fold_norm_min_rows
-    return 0 if n <= 0 else sum(14 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if bc * s >= n)
+    return 0 if n <= 0 else sum(14 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if bc * s >= n)   # (adapter sites: no extra launch)
 
 
 def _fused_ff_count(unet) -> int:

@@ -313,7 +313,7 @@ def test_step_graph_key_covers_what_a_captured_step_bakes_in(tiny_unet):
     assert s2 != s1
     adapters[1].to_v_ip.weight = torch.nn.Parameter(torch.zeros_like(adapters[1].to_v_ip.weight))
     assert den._site_state() != s2
-    assert den._site_blobs() == [None] * (2 * len(adapters))
+    assert den._site_blobs() == [None] * (3 * len(adapters))
     den.invalidate_graph()
     assert den._graph is None
 
