@@ -139,11 +139,13 @@ def test_site_with_folded_norm2_matches_oracle(shape, dtype):
     with torch.no_grad():
         norm.weight.normal_(1.0, 0.25, generator=g); norm.bias.normal_(0.0, 0.2, generator=g)
     attn, proc = build_site(case, dtype)
-    norm_d = norm.to("cuda", dtype)
+    import copy
+    norm_d = copy.deepcopy(norm).to("cuda", dtype)
     x = case["x"].to("cuda", dtype)
     ctx = case["ctx"].to("cuda", dtype)
-    assert proc.can_fold_norm(attn, x, norm_d, ctx)
+    assert not proc.can_fold_norm(attn, x, norm_d, ctx)          # autograd on: training keeps the separate LayerNorm
     with torch.no_grad():
+        assert proc.can_fold_norm(attn, x, norm_d, ctx)
         n0 = _lib.launch_count()
         y = proc(attn, x, encoder_hidden_states=ctx, fold_norm=norm_d)
         built = _lib.launch_count() - n0
