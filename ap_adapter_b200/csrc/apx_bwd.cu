@@ -289,7 +289,11 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __
         if (ox < n && oy0 + j < n) out[static_cast<size_t>(oy0 + j) * n + ox] = t[threadIdx.x][j];
 }
 
+}  // namespace
 struct BwdWs { size_t wqT, woT, q, dO, dQ, dKa, dVa, total; };
+int bwd_tail(uint8_t* ws, const BwdWs& w, const void* ctx, void* dX, float* dWk_ip, float* dWv_ip, int Bc, int S, int C, int H, int Lt, int La, int Dctx,
+             int dtype, void* stream);
+namespace {
 BwdWs bwd_ws(int Bc, int S, int C, int La) {
     BwdWs w;
     size_t off = 0;
@@ -349,6 +353,14 @@ int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo
     APX_CUDA(cudaMemsetAsync(ws + w.dKa, 0, static_cast<size_t>(Bc) * La * C * 4, st));
     APX_CUDA(cudaMemsetAsync(ws + w.dVa, 0, static_cast<size_t>(Bc) * La * C * 4, st));
 
+    if (ipattn_bwd_tc_supported(C, H, Lt, La)) {
+        // tensor-core attention backward (apx_bwd_tc.cu): contexts of up to 16 + 128 padded tokens, d % 16 == 0
+        const size_t tiles_off = 2 * align_up(static_cast<size_t>(Bc) * L * C * 2, 256);   // [K natural][V natural][tiles], see apx_api.cu
+        rc = ipattn_bwd_tc(ws + w.q, ws + w.dO, static_cast<const uint8_t*>(cache) + tiles_off, ws + w.dQ, reinterpret_cast<float*>(ws + w.dKa),
+                           reinterpret_cast<float*>(ws + w.dVa), Bc, S, C, H, Lt, La, ap_scale, dtype, st);
+        if (rc) return rc;
+        return bwd_tail(ws, w, ctx, dX, dWk_ip, dWv_ip, Bc, S, C, H, Lt, La, Dctx, dtype, stream);
+    }
     BwdArgs a;
     a.Q = reinterpret_cast<const uint16_t*>(ws + w.q);
     a.dO = reinterpret_cast<const uint16_t*>(ws + w.dO);
@@ -379,16 +391,28 @@ int apx_ipattn_bwd(const void* dY, const void* X, const void* Wq, const void* Wo
         APX_CUDA(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     fn<<<dim3(ceil_div(S, 4 * rows), H, Bc), 128, smem, st>>>(a);
     APX_LAUNCH_CHECK("ipattn_bwd_kernel");
-    rc = apx_linear(ws + w.dQ, C, ws + w.wqT, C, nullptr, nullptr, 0, dX, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
+    return bwd_tail(ws, w, ctx, dX, dWk_ip, dWv_ip, Bc, S, C, H, Lt, La, Dctx, dtype, stream);
+}
+
+}  // extern "C"
+
+namespace apx {
+// dX = dQ Wq on the tcgen05 GEMM, then the two weight gradients dW[c, k] = sum_m dK_a[m, c] E_a[m, k]
+int bwd_tail(uint8_t* ws, const BwdWs& w, const void* ctx, void* dX, float* dWk_ip, float* dWv_ip, int Bc, int S, int C, int H, int Lt, int La, int Dctx,
+             int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int M = Bc * S, L = Lt + La;
+    int rc = apx_linear(ws + w.dQ, C, ws + w.wqT, C, nullptr, nullptr, 0, dX, C, M, C, C, dtype, dtype, APX_EPI_NONE, stream);
     if (rc) return rc;
     dim3 wg(ceil_div(C, 64), ceil_div(Dctx, 64), ceil_div(Bc * La, WGRAD_MSPLIT));
     APX_CUDA(cudaMemsetAsync(dWk_ip, 0, static_cast<size_t>(C) * Dctx * 4, st));
     APX_CUDA(cudaMemsetAsync(dWv_ip, 0, static_cast<size_t>(C) * Dctx * 4, st));
-    wgrad_kernel<<<wg, 256, 0, st>>>(a.dKa, static_cast<const uint16_t*>(ctx), dWk_ip, Bc * La, C, Dctx, La, L, Lt, a.fmt);
+    const int fmt = dtype == APX_F16 ? 0 : 1;
+    wgrad_kernel<<<wg, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.dKa), static_cast<const uint16_t*>(ctx), dWk_ip, Bc * La, C, Dctx, La, L, Lt, fmt);
     APX_LAUNCH_CHECK("wgrad_kernel");
-    wgrad_kernel<<<wg, 256, 0, st>>>(a.dVa, static_cast<const uint16_t*>(ctx), dWv_ip, Bc * La, C, Dctx, La, L, Lt, a.fmt);
+    wgrad_kernel<<<wg, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.dVa), static_cast<const uint16_t*>(ctx), dWv_ip, Bc * La, C, Dctx, La, L, Lt, fmt);
     APX_LAUNCH_CHECK("wgrad_kernel");
+    (void)H;
     return APX_OK;
 }
-
-}  // extern "C"
+}  // namespace apx

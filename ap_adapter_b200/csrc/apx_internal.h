@@ -107,6 +107,11 @@ bool ipattn_site4_supported(int C, int H, int Lt, int La);
 int ipattn_site4(const void* X, const void* wpack, const void* cache_tiles, const float* bo, void* Y, int Bc, int S, int C, int H,
                  int Lt, int La, float ap_scale, int dtype, bool accumulate, cudaStream_t st);
 
+// ---- tensor-core attention backward of the adapter site (apx_bwd_tc.cu) ----------------------------------------------------------
+bool ipattn_bwd_tc_supported(int C, int H, int Lt, int La);
+int ipattn_bwd_tc(const void* Q, const void* dO, const void* cache_tiles, void* dQ, float* dKa, float* dVa, int Bc, int S, int C, int H, int Lt,
+                  int La, float ap_scale, int dtype, cudaStream_t st);
+
 // ---- CUDA-core kernels --------------------------------------------------------------------
 int gemm_simt(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
               int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
