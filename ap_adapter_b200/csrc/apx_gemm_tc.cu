@@ -49,7 +49,11 @@ struct GemmArgs {
     int64_t ldo2;         // A operand of the next GEMM when `out` is an fp32 residual stream
     const float* ln_c1;   // APX_EPI_LNFOLD: c1[n] = sum_k W'[n, k] of the gamma-folded weight (bias then holds c2[n] = sum_k beta_k W[n, k] + b[n])
     float ln_eps;
+    long long* trace;     // diagnostic (APX_GEMM_TRACE=1): clock64 stamps of CTA (0, 0, 0)
 };
+
+#define GEMM_TRACE(slot) \
+    do { if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g.trace[(slot)] = clock64(); } while (0)
 
 constexpr int LDP = 64 + 4;                        // fp32 row pitch of a staged 64-column tile in shared memory (words)
 constexpr int MAX_RECV_BYTES = 7 * 16 * LDP * 4;   // (splits - 1) slabs of 128 / splits rows, largest at splits = 8
@@ -151,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kb0 = (g.K / BK) * z / splits;
     const int num_kb = (g.K / BK) * (z + 1) / splits - kb0;
 
+    if (threadIdx.x == 0) GEMM_TRACE(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -170,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) GEMM_TRACE(1);
 
     if (warp == 0) {
         if (elect_one()) {   // elect.sync: the TMA / MMA operands stay in uniform registers (no per-instruction R2UR waterfall)
@@ -180,7 +186,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + GemmCfg<BN>::B_STAGE_BYTES);
                 tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, (kb0 + i) * BK, m0, &full_bar[s]);
                 tma_load_2d(sB + s * GemmCfg<BN>::B_STAGE_BYTES, &tmB, (kb0 + i) * BK, n0, &full_bar[s]);
+                if (i == 0) GEMM_TRACE(2);
             }
+            GEMM_TRACE(3);
         }
         __syncwarp();
         if (splits > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -192,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (i == 0) GEMM_TRACE(4);
                 const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
                 const uint32_t b_addr = smem_u32(sB + s * GemmCfg<BN>::B_STAGE_BYTES);
 #pragma unroll
@@ -204,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
             }
             umma_commit(acc_bar);  // accumulator complete
+            GEMM_TRACE(5);
         }
         __syncwarp();
         if (splits > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -254,6 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
                     }
                 }
+                asm volatile("fence.acq_rel.cta;" : "+f"(s1), "+f"(s2) : : "memory");   // the loads above have RETURNED before the stage is released (see apx_gemm16.cu)
                 mbar_arrive(&empty_bar[s]);
             }
             const float inv_k = 1.0f / static_cast<float>(g.K);
@@ -261,6 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sStat[trow] = make_float2(shift + m, rsqrtf(fmaxf(s2 * inv_k - m * m, 0.f) + g.ln_eps));
             // the accumulator tile is staged OVER the pipeline stages below: every statistics thread must be done reading them
             named_bar_sync(1, 128);
+            if (te == 0) GEMM_TRACE(6);
         }
         Res8 cur;
         cur.a = make_uint4(0, 0, 0, 0); cur.b = cur.a;
@@ -268,6 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
         mbar_wait(acc_bar, 0);
         tc_fence_after();
+        if (te == 0) GEMM_TRACE(7);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         float* sP = reinterpret_cast<float*>(smem);   // over the pipeline stages: every MMA that read them has completed
 #pragma unroll 2
@@ -284,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers' mbarriers are initialised (long since)
         }
         named_bar_sync(1, 128);
+        if (te == 0) GEMM_TRACE(8);
         if (splits > 1) {
             // every peer gets the rows it finishes; slot of sender z in receiver p: z < p ? z : z - 1
             const uint32_t slab_bytes = static_cast<uint32_t>(rows_per) * LDT * 4;
@@ -295,6 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(recv_bar, 0);
             if (te < splits && te != z) mbar_arrive_remote(map_to_cta(smem_u32(done_bar), te));   // "I hold all my slabs"
+            if (te == 0) GEMM_TRACE(9);
         }
 #pragma unroll 1
         for (int rl = r0; rl < rows_per; rl += ROWS_STEP) {
@@ -319,12 +334,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             cur = nxt;
         }
+        if (te == 0) GEMM_TRACE(10);
         if (splits > 1) mbar_wait(done_bar, 0);   // nobody is still reading this CTA's shared memory
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) GEMM_TRACE(11);
     if (warp == 1) tmem_dealloc<BN>(tmem_base);
+    if (threadIdx.x == 32) GEMM_TRACE(12);
 }
 
 template <int BN>
@@ -382,10 +400,13 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
     APX_REQUIRE(!(epilogue & APX_EPI_RES16) || out_dtype != APX_F32, APX_EINVAL, "gemm_tc: APX_EPI_RES16 needs a 16-bit out_dtype");
     APX_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, APX_EINVAL, "gemm_tc: bias alignment");
 
+    APX_REQUIRE(!out2 || (ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0), APX_EINVAL, "gemm_tc: out2 alignment");
     // Wide tiles once the grid already fills the machine, narrow ones otherwise; split-K clusters when even those leave SMs idle.
     const bool wide = (N % 128 == 0) && (static_cast<int64_t>(ceil_div(M, BM)) * (N / 128) >= 148);
     APX_REQUIRE(!(epilogue & APX_EPI_LNFOLD) || (ln_c1 && bias && (reinterpret_cast<uintptr_t>(ln_c1) & 15) == 0), APX_EINVAL,
                 "gemm_tc: APX_EPI_LNFOLD needs c1 and c2 (16-byte aligned)");
+    if (gemm16_supported(residual, out_dtype, in_dtype, epilogue, out2))
+        return gemm16(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, epilogue, st, ln_c1, ln_eps);
     // the row statistics of a folded LayerNorm are taken over the CTA's whole K range: no split-K
     const int splits = (wide || (epilogue & APX_EPI_LNFOLD)) ? 1 : pick_splits(M, N, K);
     const int BN = wide ? 128 : 64;
@@ -405,9 +426,27 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
         int rc = encode_tmap(&tmB, in_dtype, 2, W, dims, strides, box, 1);
         if (rc) return rc;
     }
-    APX_REQUIRE(!out2 || (ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0), APX_EINVAL, "gemm_tc: out2 alignment");
-    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits, out2, ldo2, ln_c1, ln_eps};
-    return wide ? launch_gemm<128>(tmA, tmB, g, st) : launch_gemm<64>(tmA, tmB, g, st);
+    GemmArgs g{bias, residual, ldr, out, ldo, M, N, K, in_dtype == APX_F16 ? 0 : 1, out_dtype, epilogue, splits, out2, ldo2, ln_c1, ln_eps, nullptr};
+    // diagnostic timeline (APX_GEMM_TRACE=1): synchronises and prints, never enabled on the product path
+    static const bool trace_on = [] { const char* e = getenv("APX_GEMM_TRACE"); return e && e[0] == '1'; }();
+    static long long* trace_buf = nullptr;
+    if (trace_on) {
+        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
+        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 16 * sizeof(long long), st));
+        g.trace = trace_buf;
+    }
+    const int rc = wide ? launch_gemm<128>(tmA, tmB, g, st) : launch_gemm<64>(tmA, tmB, g, st);
+    if (trace_on && rc == APX_OK) {
+        long long t[16];
+        APX_CUDA(cudaStreamSynchronize(st));
+        APX_CUDA(cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost));
+        auto rel = [&](int slot) { return t[slot] ? t[slot] - t[0] : -1; };
+        printf("[apx gemm trace] M=%d N=%d K=%d BN=%d splits=%d epi=%d | setup %lld | tma first %lld all %lld | mma first_full %lld committed %lld | "
+               "epi stats %lld acc_seen %lld staged %lld exchanged %lld stored %lld | sync %lld dealloc %lld (cycles, CTA 0)\n",
+               M, N, K, BN, splits, epilogue, rel(1), rel(2), rel(3), rel(4), rel(5), rel(6), rel(7), rel(8), rel(9), rel(10), rel(11), rel(12));
+        fflush(stdout);
+    }
+    return rc;
 }
 
 }  // namespace apx

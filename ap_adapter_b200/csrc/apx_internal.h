@@ -50,6 +50,10 @@ int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const ui
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
             cudaStream_t st, const float* ln_c1 = nullptr, float ln_eps = 0.f, void* out2 = nullptr, int64_t ldo2 = 0);
+// 16-bit-output specialisation (apx_gemm16.cu); gemm_tc routes to it when gemm16_supported()
+bool gemm16_supported(const float* residual, int out_dtype, int in_dtype, int epilogue, const void* out2);
+int gemm16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* residual, int64_t ldr, void* out,
+           int64_t ldo, int M, int N, int K, int dtype, int epilogue, cudaStream_t st, const float* ln_c1, float ln_eps);
 
 // Packed per-(batch, head) K / V^T tiles in UMMA no-swizzle K-major core-matrix order.
 // Per (batch, head) the cache holds three tiles: K, V^T, and V^T extended by 16 rows of which the first (row d_pad) is all ones

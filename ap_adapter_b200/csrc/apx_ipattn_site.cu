@@ -425,6 +425,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const float inv = 1.0f / static_cast<float>(a.C), m = s1 * inv;
                 ln_mean = shift + m;
                 ln_rstd = rsqrtf(fmaxf(s2 * inv - m * m, 0.f) + a.ln_eps);
+                asm volatile("fence.acq_rel.cta;" : "+f"(s1), "+f"(s2) : : "memory");   // the loads have RETURNED before the stages are released (measured in apx_gemm16.cu)
                 mbar_arrive(&bars[B_STAT]);
                 mbar_wait_nocall(&bars[B_STAT], 0);   // the Q tile below is written OVER the phase-A stages: every row must have been read
             }

@@ -61,7 +61,7 @@ def test_geglu_epilogue_agrees_with_cuda_core_gemm():
 def test_block_takes_fused_route_and_matches_unfused():
     torch.manual_seed(5)
     blk = BasicTransformerBlock(256, 4, 64, cross_attention_dim=None, double_self_attention=False).eval().half().cuda()
-    h = torch.randn(2, 500, 256, device="cuda", dtype=torch.float16)
+    h = torch.randn(2, 400, 256, device="cuda", dtype=torch.float16)      # 800 rows: below the Q(KV) LayerNorm-fold threshold
     with torch.no_grad():
         BasicTransformerBlock.fold_residual = True
         try:
@@ -125,8 +125,11 @@ def test_plain_site_folds_to_out_and_residual_into_one_gemm(c, heads, s, cross):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
 @pytest.mark.parametrize("m,k,n,geglu,res", [(2000, 256, 2048, True, False), (504, 384, 3072, True, False), (128, 640, 5120, True, False),
-                                             (333, 256, 768, False, True), (1026, 768, 2304, False, False)],
-                         ids=["ff256", "ff384", "ff640", "qkv_res", "vit_qkv"])
+                                             (333, 256, 768, False, True), (1026, 768, 2304, False, False),
+                                             (128, 640, 1920, False, False), (100, 640, 640, False, True), (70, 1024, 256, True, True),
+                                             (2500, 256, 1024, False, True)],
+                         ids=["ff256", "ff384", "ff640", "qkv_res", "vit_qkv", "qkv640_splitk", "q640_splitk_res", "geglu_splitk_res",
+                              "wide_res"])
 def test_linear_with_folded_layernorm_matches_torch(m, k, n, geglu, res, dtype):
     """apx_linear_lnfold (LayerNorm of the A rows folded into the tcgen05 GEMM: statistics from the A tiles in shared memory, correction
     in the epilogue) against LayerNorm -> Linear (-> GEGLU) in fp32 on the same 16-bit operands."""
@@ -138,12 +141,12 @@ def test_linear_with_folded_layernorm_matches_torch(m, k, n, geglu, res, dtype):
     w = (torch.randn(n, k, generator=g) * k ** -0.5).to(dtype)
     b = torch.randn(n, generator=g) * 0.2
     gamma, beta = 1.0 + 0.3 * torch.randn(k, generator=g), 0.2 * torch.randn(k, generator=g)
-    r = torch.randn(m, n, generator=g).to(dtype) if res else None
+    r = torch.randn(m, n // 2 if geglu else n, generator=g).to(dtype) if res else None
     ref = F.linear(F.layer_norm(x.float(), (k,), gamma, beta, 1e-5), w.float(), b)
     if geglu:
         ref = ref[:, 0::2] * F.gelu(ref[:, 1::2])
     if res:
-        ref = ref + r.float()
+        ref = ref.to(dtype).float() + r.float()
     wg, c1, c2 = _lib.fold_layernorm(w.cuda(), b.cuda(), gamma.cuda(), beta.cuda())
     n0 = _lib.launch_count()
     y = _lib.linear_lnfold(x.cuda(), wg, c1, c2, 1e-5, residual=r.cuda() if res else None, geglu=geglu)
@@ -167,3 +170,37 @@ def test_feedforward_with_folded_norm_matches_separate_layernorm():
         b = ff.fused(norm(h), h)
         ref = ff.float()(torch.nn.functional.layer_norm(h.float(), (384,), norm.weight.float(), norm.bias.float(), norm.eps)) + h.float()
     assert rel_err(a, ref) < 2e-3 and rel_err(b, ref) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("m,k,n,act,res", [(2000, 256, 256, "none", True), (504, 384, 384, "none", True), (128, 640, 640, "none", True),
+                                           (2000, 1024, 256, "none", True), (126, 2560, 640, "none", False), (4104, 768, 3072, "gelu", False),
+                                           (513, 768, 3072, "gelu", False), (3000, 256, 512, "none", True), (300, 128, 512, "geglu", True),
+                                           (1, 64, 64, "none", False), (129, 64, 128, "geglu", False)],
+                         ids=["to_out256", "to_out384", "to_out640", "ff_out256", "ff_out640", "vit_fc1_b8", "vit_fc1_b1", "wide_res", "geglu_res",
+                              "one_row", "two_tiles"])
+def test_linear_16bit_epilogues_match_torch(m, k, n, act, res, dtype):
+    """apx_linear with a 16-bit output (the row-per-thread TMA-store epilogue and the cluster split-K finisher of apx_gemm16.cu) against
+    fp32 torch on the same 16-bit operands: bias, GELU / GEGLU, 16-bit residual with the caller's double rounding."""
+    import torch.nn.functional as F
+    from ap_adapter_b200 import _lib
+    from gpu_util import record, rel_err
+    g = torch.Generator().manual_seed(m * 7 + n)
+    x = torch.randn(m, k, generator=g).to(dtype)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(dtype)
+    b = torch.randn(n, generator=g) * 0.2
+    n_out = n // 2 if act == "geglu" else n
+    r = torch.randn(m, n_out, generator=g).to(dtype) if res else None
+    ref = F.linear(x.float(), w.float(), b)
+    if act == "geglu":
+        ref = ref[:, 0::2] * F.gelu(ref[:, 1::2])
+    elif act == "gelu":
+        ref = F.gelu(ref)
+    if res:
+        ref = ref.to(dtype).float() + r.float()
+    n0 = _lib.launch_count()
+    y = _lib.linear(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda() if res else None, gelu=act == "gelu", geglu=act == "geglu")
+    assert _lib.launch_count() - n0 == 1 and y.shape == (m, n_out)
+    err = rel_err(y, ref)
+    record(f"linear16/{m}x{k}x{n}/{act}", dtype=str(dtype), err=err)
+    assert err < (1.5e-3 if dtype == torch.float16 else 1.2e-2)   # one or two roundings to the 16-bit output type
