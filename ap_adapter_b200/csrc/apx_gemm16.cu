@@ -445,15 +445,16 @@ Gemm16Fn pick_act(int act, bool ln, int fmt) {
                                                                                                : pick_ln<BN, APX_EPI_NONE>(ln, fmt);
 }
 
-// Split-K factor: only when the 128 x 64 tiling leaves most of the 148 SMs idle, at least two k-blocks per CTA, and the grid stays
-// within two CTAs per SM.  APX_GEMM_SPLITK=n forces n (1 turns it off).
+// Split-K factor, from the B200 timings of the UNet's token GEMMs (tools/time_gemm_step.py with APX_GEMM_SPLITK=1/2/4, profiles/
+// r2k_gemm_splitk.txt): the slab exchange and the narrower finisher cost about 0.75 us, a k-block about 0.23 us, so splitting pays
+// from 8 k-blocks (K >= 512) and only while every CTA of the cluster still gets an SM of its own.  APX_GEMM_SPLITK=n forces n.
 int pick_splits16(int M, int N, int K) {
     static const int forced = [] { const char* e = getenv("APX_GEMM_SPLITK"); return e ? atoi(e) : 0; }();
     const int tiles = ceil_div(M, BM) * (N / 64), num_kb = K / BK;
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced <= num_kb ? forced : 1;
-    if (tiles >= 148) return 1;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return 2 * forced <= num_kb || forced == 1 ? forced : 1;
+    if (num_kb < 8) return 1;
     for (int s = 8; s >= 2; s >>= 1)
-        if (2 * s <= num_kb && tiles * s <= 2 * 148) return s;
+        if (2 * s <= num_kb && tiles * s <= 148) return s;
     return 1;
 }
 

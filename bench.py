@@ -526,10 +526,32 @@ def run_ours(args) -> dict:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        # ---- device-resident timing -----------------------------------------------------------------
+        # ---- warm-up + clocks ---------------------------------------------------------------------------------------
+        # Clocks under load: nvidia-smi polling costs the polled GPU several per cent (round 1: the sampled loop read 8 % slower than
+        # the unsampled one), so the sampler runs over an IDENTICAL UNTIMED repeat of the loop, not over the timed regions.  The repeat
+        # runs BEFORE them: a timed loop that starts 50 ms after the first launch reads 3 - 6 % slower than the same loop a second
+        # later (profiles/r2k: 9.74 ms/step over 50 steps, 9.41 over 400), so the >= 1.5 s repeat doubles as the warm-up.
         graph["latents"].copy_(lat0)
         for i in range(max(3, args.warmup)):
             step(i)
+        barrier()
+        w_est0 = time.perf_counter()
+        for i in range(20):
+            step(i)
+        barrier()
+        ms_est = (time.perf_counter() - w_est0) * 1e3 / 20
+        graph["latents"].copy_(lat0)
+        with ClockSampler(local) as clk:
+            barrier()
+            w0 = time.perf_counter()
+            for i in range(max(args.steps, int(1500 / max(ms_est, 1e-3)))):   # >= 1.5 s under load: several 200 ms samples
+                step(i)
+            barrier()
+            w1 = time.perf_counter()
+        clocks = clk.summary(w0, w1)
+        clocks["sampled"] = "during an identical untimed repeat of the timed loop, run right before it (polling perturbs the polled GPU)"
+
+        # ---- device-resident timing -----------------------------------------------------------------
         graph["latents"].copy_(lat0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -541,18 +563,6 @@ def run_ours(args) -> dict:
         barrier()
         ms = e0.elapsed_time(e1)
         assert torch.isfinite(final).all(), "non-finite latents"
-        # Clocks under load: nvidia-smi polling costs the polled GPU several per cent (round 1: the sampled loop read 8 % slower than
-        # the unsampled one), so the sampler runs over an IDENTICAL UNTIMED repeat of the loop, not over the timed regions.
-        graph["latents"].copy_(lat0)
-        with ClockSampler(local) as clk:
-            barrier()
-            w0 = time.perf_counter()
-            for i in range(max(args.steps, int(1500 / max(ms / args.steps, 1e-3)))):   # >= 1.5 s under load: several 200 ms samples
-                step(i)
-            barrier()
-            w1 = time.perf_counter()
-        clocks = clk.summary(w0, w1)
-        clocks["sampled"] = "during an identical untimed repeat of the timed loop (polling perturbs the polled GPU)"
         shard_check = shard_equality_check(den, graph, final, b, world, rank, dev, ts, coefs, args.steps) if world > 1 else None
 
         # ---- end to end: the step's latents come from and go back to pinned host memory every step ------------------
