@@ -48,6 +48,14 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+void add_pdl_attr(cudaLaunchAttribute* attrs, unsigned* n) {
+    static const bool on = [] { const char* e = getenv("APX_PDL"); return !(e && e[0] == '0'); }();
+    if (!on) return;
+    attrs[*n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[*n].val.programmaticStreamSerializationAllowed = 1;
+    ++*n;
+}
+
 int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
     EncodeTiledFn fn = get_encode_fn();

@@ -187,7 +187,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 1) tmem_alloc<BN>(tmem_slot);
     tc_fence_before();
     if (splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // "my mbarriers exist"
+    pdl_wait();                 // everything above is on-chip set-up; from here on the predecessor's results are read
     __syncthreads();
+    pdl_launch_dependents();    // this CTA holds its tensor memory: the next kernel may start its own set-up
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) G16_TRACE(1);
@@ -526,13 +528,14 @@ int gemm16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* 
     static const bool one_cta = [] { const char* e = getenv("APX_G16_ONE_CTA"); return e && e[0] == '1'; }();   // diagnostic: one CTA per SM
     cfg.dynamicSmemBytes = (wide ? Cfg<128>::SMEM_BYTES : Cfg<64>::SMEM_BYTES) + ((splits > 1 || one_cta) ? RECV_BYTES : 0);
     cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 1;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = static_cast<unsigned>(splits);
-    cfg.attrs = &attr;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 1;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = static_cast<unsigned>(splits);
+    cfg.attrs = attrs;
     cfg.numAttrs = splits > 1 ? 1 : 0;
+    add_pdl_attr(attrs, &cfg.numAttrs);
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, g));
     APX_LAUNCH_CHECK("gemm16_kernel");
     if (trace_on) {

@@ -172,7 +172,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     // cluster barrier phase 1: "my mbarriers exist".  The matching wait sits right before each warp's first remote operation / exit.
     if (splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    pdl_wait();                 // programmatic dependent launch: on-chip set-up above, the predecessor's results below
     __syncthreads();
+    pdl_launch_dependents();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) GEMM_TRACE(1);
@@ -357,13 +359,14 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& 
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES + (g.splits > 1 ? (g.splits - 1) * (BM / g.splits) * LDP * 4 : 0);
     cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 1;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = static_cast<unsigned>(g.splits);
-    cfg.attrs = &attr;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 1;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = static_cast<unsigned>(g.splits);
+    cfg.attrs = attrs;
     cfg.numAttrs = g.splits > 1 ? 1 : 0;
+    add_pdl_attr(attrs, &cfg.numAttrs);
     APX_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, tmA, tmB, g));
     APX_LAUNCH_CHECK("gemm_tc_kernel");
     return APX_OK;

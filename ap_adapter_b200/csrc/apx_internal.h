@@ -37,6 +37,8 @@ void count_launch(int n = 1);
 // cudaFuncSetAttribute is PER DEVICE: `mask` (one per call site) has one bit per device ordinal; true on the first call on the
 // current device (thread-safe; ordinals >= 64 simply set the attribute every time).
 bool first_use_on_device(std::atomic<uint64_t>& mask);
+// Appends the programmatic-dependent-launch attribute (APX_PDL=0 turns it off) to a launch whose kernel calls pdl_wait().
+void add_pdl_attr(cudaLaunchAttribute* attrs, unsigned* n);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    ceil_div(int a, int b) { return (a + b - 1) / b; }

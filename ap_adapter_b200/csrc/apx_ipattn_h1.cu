@@ -155,11 +155,13 @@ ipattn_site_h1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc<512>(tmem_slot);
+    pdl_wait();   // programmatic dependent launch: set-up above, global reads below
     if (threadIdx.x < 128) {
         for (int i = threadIdx.x; i < a.d_pad; i += 128) sBias[i] = (a.bo && i < a.d) ? a.bo[h * a.d + i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
+    pdl_launch_dependents();
     tc_fence_after();
     if (clustered) cluster_arrive();   // #1: this CTA's barriers exist (waited for before the first remote operation)
     const uint32_t tmem_base = *tmem_slot;
@@ -656,13 +658,14 @@ int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, co
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = static_cast<unsigned>(H);
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = static_cast<unsigned>(H);
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
     cfg.numAttrs = H > 1 ? 1 : 0;
+    add_pdl_attr(attrs, &cfg.numAttrs);
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmY, a));
     APX_LAUNCH_CHECK("ipattn_site_h1_kernel");
     if (trace_on) {

@@ -175,6 +175,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc<512>(tmem_slot);
+    pdl_wait();   // programmatic dependent launch: barrier init / tensor-memory allocation above overlap the predecessor's tail
     float* sLn = sBias + a.C;            // [2][Nq]: c1, c2 of the folded LayerNorm in the padded head layout
     if (threadIdx.x < 256) {
         for (int i = threadIdx.x; i < a.C; i += 256) sBias[i] = a.bo ? a.bo[i] : 0.f;
@@ -189,6 +190,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    pdl_launch_dependents();
     tc_fence_after();
     // Cluster handshake before the first remote write into a peer: every CTA's barriers must exist AND its phase-A stages (which
     // overlay sQO) must be dead.  The warpgroup warps arrive once they have seen the Q accumulator complete, the other warps
@@ -814,13 +816,14 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = p.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = static_cast<unsigned>(cs);
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = static_cast<unsigned>(cs);
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
     cfg.numAttrs = cs > 1 ? 1 : 0;
+    add_pdl_attr(attrs, &cfg.numAttrs);
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmY, a));
     APX_LAUNCH_CHECK("ipattn_site_kernel");
     if (trace_on) {

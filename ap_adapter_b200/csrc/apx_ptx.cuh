@@ -97,6 +97,15 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream still
+// runs: pdl_wait() blocks until every prerequisite grid has COMPLETED and its memory is visible (a no-op for a normal launch), so
+// everything before it must stay on chip (barrier init, TMEM allocation, descriptor prefetch).  pdl_launch_dependents() lets the
+// NEXT such kernel begin that prologue; call it once this CTA holds its own tensor memory (a dependent that allocated first could
+// starve it).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
