@@ -202,8 +202,11 @@ int apx_ctx_kv(const void* ctx, const void* Wk, const void* Wv, const void* Wk_i
     const void* Ws[4] = {Wk, Wv, Wk_ip, Wv_ip};
     void* outs[4] = {kt, vt, ka, va};
     for (int i = 0; i < 4; ++i) {
-        int rc = apx_linear(ctx, Dctx, Ws[i], Dctx, nullptr, nullptr, 0, outs[i], C, M, C, Dctx, dtype, dtype,
-                            APX_EPI_NONE, stream);
+        // never split along K: a context row's K / V must not depend on how many rows (clips) the call carries — the sharded run
+        // reproduces the single-GPU run bit for bit (tests/test_gpu_ipattn.py::test_full_size_properties_batch8)
+        int rc = current_impl() == APX_IMPL_SIMT
+                     ? apx_linear(ctx, Dctx, Ws[i], Dctx, nullptr, nullptr, 0, outs[i], C, M, C, Dctx, dtype, dtype, APX_EPI_NONE, stream)
+                     : gemm_tc(ctx, Dctx, Ws[i], Dctx, nullptr, nullptr, 0, outs[i], C, M, C, Dctx, dtype, dtype, APX_EPI_NOSPLIT, st);
         if (rc) return rc;
     }
     uint8_t* cb = static_cast<uint8_t*>(cache);

@@ -474,7 +474,7 @@ int gemm16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* 
     const int act = epilogue & 3;
     const bool ln = (epilogue & APX_EPI_LNFOLD) != 0;
     const bool wide = (N % 128 == 0) && (static_cast<int64_t>(ceil_div(M, BM)) * (N / 128) >= 148);
-    const int splits = wide ? 1 : pick_splits16(M, N, K);
+    const int splits = (wide || (epilogue & APX_EPI_NOSPLIT)) ? 1 : pick_splits16(M, N, K);
     const int BN = wide ? 128 : 64;
     const int n_out = act == APX_EPI_GEGLU ? N / 2 : N;
     const int out_cols = act == APX_EPI_GEGLU ? BN / 2 : BN;

@@ -411,7 +411,7 @@ int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float*
     if (gemm16_supported(residual, out_dtype, in_dtype, epilogue, out2))
         return gemm16(A, lda, W, ldw, bias, residual, ldr, out, ldo, M, N, K, in_dtype, epilogue, st, ln_c1, ln_eps);
     // the row statistics of a folded LayerNorm are taken over the CTA's whole K range: no split-K
-    const int splits = (wide || (epilogue & APX_EPI_LNFOLD)) ? 1 : pick_splits(M, N, K);
+    const int splits = (wide || (epilogue & (APX_EPI_LNFOLD | APX_EPI_NOSPLIT))) ? 1 : pick_splits(M, N, K);
     const int BN = wide ? 128 : 64;
 
     CUtensorMap tmA, tmB;

@@ -52,6 +52,8 @@ int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const ui
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
             cudaStream_t st, const float* ln_c1 = nullptr, float ln_eps = 0.f, void* out2 = nullptr, int64_t ldo2 = 0);
+// internal epilogue flag: never split K (the context projections: a row's value must not depend on how many rows the call has)
+#define APX_EPI_NOSPLIT 16
 // 16-bit-output specialisation (apx_gemm16.cu); gemm_tc routes to it when gemm16_supported()
 bool gemm16_supported(const float* residual, int out_dtype, int in_dtype, int epilogue, const void* out2);
 int gemm16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* residual, int64_t ldr, void* out,

@@ -665,7 +665,8 @@ int ipattn_site_h1(const void* X, const void* wpack, const void* cache_tiles, co
     attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = H > 1 ? 1 : 0;
-    add_pdl_attr(attrs, &cfg.numAttrs);
+    // no programmatic-launch attribute on the site kernel itself: its predecessor in the step is a PyTorch kernel (nothing to overlap), and
+    // back-to-back site launches overlapping each other would flatter the kernel's stand-alone timing.  It still TRIGGERS its dependents.
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmX, tmY, a));
     APX_LAUNCH_CHECK("ipattn_site_h1_kernel");
     if (trace_on) {

@@ -186,6 +186,60 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def gemm_roofline(batch: int, iters: int = 30) -> dict:
+    """The kernel with the largest share of the step's device time after the site kernels: libapx's GEMM, at its heaviest call of
+    the step — the C = 256 FeedForward projection with norm3 folded in and the GEGLU epilogue (40 calls per step).  Same method as
+    site_roofline: CUDA events around replays of a graph that rotates over operand copies larger than the L2."""
+    from ap_adapter_b200 import _lib
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m, n, k = 2 * batch * 1000, 2048, 256
+    per_copy = 2 * (m * k + n * k) + 2 * m * (n // 2)
+    r = max(4, min(256, int(2.5 * 126e6 / per_copy) + 1))
+    g = torch.Generator(device=dev).manual_seed(1)
+    a = torch.randn(r, m, k, generator=g, device=dev, dtype=torch.float16)
+    w = torch.randn(r, n, k, generator=g, device=dev, dtype=torch.float16) * k ** -0.5
+    bias = torch.zeros(n, device=dev, dtype=torch.float16)
+    gamma, beta = torch.ones(k, device=dev, dtype=torch.float16), torch.zeros(k, device=dev, dtype=torch.float16)
+    folded = [_lib.fold_layernorm(w[i], bias, gamma, beta) for i in range(r)]
+
+    def launch(i):
+        wg, c1, c2 = folded[i]
+        return _lib.linear_lnfold(a[i], wg, c1, c2, 1e-5, geglu=True)
+
+    for i in range(r):
+        launch(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = [launch(i) for i in range(r)]   # kept alive: the graph's private pool owns them
+    for _ in range(3):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    del outs
+    us = 1e3 * e0.elapsed_time(e1) / (iters * r)
+    flops = 2.0 * m * n * k
+    byts = per_copy + 8 * n
+    pk = peaks()
+    t_tensor, t_hbm = flops / (pk["tflops"] * 1e12), byts / (pk["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_tensor >= t_hbm else "hbm"
+    if bound == "tensor":
+        achieved, peak, unit = flops / (us * 1e-6) / 1e12, pk["tflops"], "TFLOP/s"
+    else:
+        achieved, peak, unit = byts / (us * 1e-6) / 1e9, pk["hbm_gbs"], "GB/s"
+    return {"kernel": f"gemm16_kernel<128, GEGLU, LN> via apx_linear_lnfold: LayerNorm + Linear + GEGLU of the C=256 FeedForward, M={m} N={n} K={k} fp16",
+            "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4), "traffic": None,
+            "us_per_call": round(us, 2), "algorithmic_bytes": byts, "algorithmic_flops": flops,
+            "floor_us": round(max(t_tensor, t_hbm) * 1e6, 3), "peak_source": pk["source"], "operand_copies_rotated": r,
+            "calls_per_step": 40}
+
+
 def site_roofline(batch: int, iters: int = 30) -> dict:
     """The dominant kernel of the hot path: the adapter site at the S=1000, C=256 geometry (10 of the 32 sites, and the
     one that moves the most bytes).  Timed through apx_ipattn_fwd with CUDA events around replays of a CUDA graph that
@@ -611,6 +665,10 @@ def run_ours(args) -> dict:
         out["shard_check"] = shard_check
     if rank == 0 and WORKLOAD == "step":
         out["roofline"] = site_roofline(b)
+        try:
+            out["roofline_gemm"] = gemm_roofline(b)
+        except Exception as exc:  # noqa: BLE001
+            out["roofline_gemm"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         out["audiomae"] = audiomae_timing()
         try:   # the fair same-box comparison; informational, never allowed to break the bench line
             out["torch_gpu"] = torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps=min(args.steps, 50))
