@@ -46,6 +46,7 @@ SYMBOLS = {
     "apx_linear": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "apx_linear_lnfold": (_I, [_P, _L, _P, _L, _P, _P, _F, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "apx_attention": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P]),
+    "apx_flash_attention": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
     "apx_ctx_kv_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "apx_ctx_kv_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "apx_ctx_kv": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
@@ -242,6 +243,27 @@ def linear_lnfold(a: torch.Tensor, wg: torch.Tensor, c1: torch.Tensor, c2: torch
         check(lib.apx_linear_lnfold(ptr(a), a.stride(0), ptr(wg), wg.stride(0), ptr(c1), ptr(c2), float(eps), ptr(residual),
                                     residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
                                     dtype_code(a.dtype), dtype_code(out.dtype), epi, stream_ptr()), "apx_linear_lnfold")
+    return out
+
+
+def flash_attention_ok(channels: int, heads: int) -> bool:
+    """Head sizes apx_flash_attention covers (d % 16 == 0, 16 <= d <= 80)."""
+    d = channels // heads if heads > 0 and channels % heads == 0 else 0
+    return d % 16 == 0 and 16 <= d <= 80
+
+
+def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(d)) v on token-major (B, S, H*d) / (B, L, H*d) views, any number of keys (apx_flash_attention)."""
+    lib = load()
+    dev = require_cuda(q, k, v)
+    assert q.dim() == 3 and k.dim() == 3 and v.dim() == 3 and k.shape == v.shape and q.shape[0] == k.shape[0] and q.shape[2] == k.shape[2]
+    assert q.dtype == k.dtype == v.dtype and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    b, s, c = q.shape
+    out = torch.empty((b, s, c), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.apx_flash_attention(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0),
+                                      v.stride(1), ptr(out), out.stride(0), out.stride(1), b, s, k.shape[1], c, heads,
+                                      dtype_code(q.dtype), stream_ptr()), "apx_flash_attention")
     return out
 
 

@@ -53,6 +53,13 @@ class AttnProcessor2_0(nn.Module):
     # least this many query rows (measured on B200 at B = 1, ms per step: fold everywhere 10.34, >= 400 rows 10.44, >= 1000 rows 9.94,
     # nowhere 10.11 — below ~1000 rows the unsplit tcgen05 GEMM loses to cuBLAS's split-K + a separate LayerNorm); APX_LN_FOLD_QKV=0 disables
     fold_norm_min_rows = int(os.environ.get("APX_LN_FOLD_QKV", "1000"))
+    # inference on CUDA: the unmasked SDPA of a site with at least this many keys runs in libapx (apx_flash_attention) instead of
+    # torch's cuDNN SDPA; APX_FLASH_ATTN=0 disables, APX_FLASH_ATTN=n sets the threshold
+    flash_min_keys = (lambda v: 1 << 30 if v == "0" else int(v))(os.environ.get("APX_FLASH_ATTN", "200"))
+    # ... and only while its grid (one CTA per 128-query tile, head and batch element) fits one wave of the 148 SMs: measured on B200,
+    # 13.7 vs 14.2 us (cuDNN) at B = 2, S = 1000, C = 256 and 6.4 vs 6.8 us at S = 252, C = 384, but 92 vs 49 us at B = 16 (one
+    # 227-register CTA per SM: nothing overlaps its latencies once there is more than one wave)
+    flash_max_ctas = int(os.environ.get("APX_FLASH_MAX_CTAS", "160"))
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
@@ -168,12 +175,20 @@ class AttnProcessor2_0(nn.Module):
             encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
         query, key, value = self._project(attn, hidden_states, encoder_hidden_states, self_attention, fold_norm)
         head_dim = key.shape[-1] // attn.heads
-        query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
-        key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
-        value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
-        hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
-                                                       is_causal=False)
-        hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+        if (attention_mask is None and query.is_cuda and not torch.is_grad_enabled() and key.shape[1] >= self.flash_min_keys
+                and batch_size * attn.heads * ((query.shape[1] + 127) // 128) <= self.flash_max_ctas and query.dtype in (torch.float16, torch.bfloat16) and query.dim() == 3 and key.dtype == query.dtype
+                and _lib.flash_attention_ok(key.shape[-1], attn.heads) and query.stride(2) == 1 and key.stride(2) == 1
+                and value.stride(2) == 1):
+            # the unmasked SDPA (reference :267-274) in libapx: keys streamed through tcgen05 in blocks of 128, straight from the
+            # (possibly strided) q / k / v slices of the fused projection; the output is already token-major [B, S, C]
+            hidden_states = _lib.flash_attention(query, key, value, attn.heads)
+        else:
+            query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+            key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+            value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+            hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
+                                                           is_causal=False)
+            hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
         out_proj = attn.to_out[0]
         if (residual_inout is not None and input_ndim == 3 and hidden_states.is_cuda and not torch.is_grad_enabled()
                 and hidden_states.dtype in (torch.float16, torch.bfloat16) and out_proj.weight.dtype == hidden_states.dtype

@@ -163,6 +163,12 @@ int apx_linear_lnfold(const void* A, int64_t lda, const void* Wg, int64_t ldw, c
                    static_cast<cudaStream_t>(stream), c1, eps);
 }
 
+int apx_flash_attention(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V, int64_t v_bs,
+                        int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int L, int C, int H, int dtype, void* stream) {
+    APX_REQUIRE(Q && K && V && O, APX_EINVAL, "apx_flash_attention: null pointer");
+    return flash_attn(Q, q_bs, q_rs, K, k_bs, k_rs, V, v_bs, v_rs, O, o_bs, o_rs, B, S, L, C, H, dtype, static_cast<cudaStream_t>(stream));
+}
+
 int apx_attention(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V,
                   int64_t v_bs, int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int H, int d, int L,
                   int L0, float w0, float w1, int dtype, void* stream) {

@@ -35,7 +35,11 @@ struct FaArgs {
     float scale_log2;        // log2(e) / sqrt(d)
     uint32_t tile_bytes;     // 128 * d * 2: a Q tile, a K block, a V block
     uint32_t off_k, off_v, off_p, off_bar;
+    long long* trace;        // diagnostic (APX_FLASH_TRACE=1): clock64 stamps of thread 0 of CTA (0,0,0), 4 per key block
 };
+
+#define FA_TRACE(slot) \
+    do { if (a.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.trace[(slot)] = clock64(); } while (0)
 
 enum { B_Q = 0, B_KV_FULL = 1, B_KV_FREE = 4, B_S_FULL = 7, B_S_FREE = 9, B_P_FULL = 11, B_PV_FULL = 13, B_PV_FREE = 15, B_COUNT = 17 };
 
@@ -43,7 +47,7 @@ __device__ __forceinline__ uint32_t idesc_major(int fmt, int M, int N, int a_mn,
     return umma_idesc_f16(fmt, M, N) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16);
 }
 
-template <int FMT>
+template <int FMT, int NG>
 __global__ void __launch_bounds__(NT, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                   FaArgs a) {
@@ -59,6 +63,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
 
+    FA_TRACE(63);
     if (threadIdx.x == 160) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
@@ -94,7 +99,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     } else if (warp == 4) {
         if (elect_one()) {
             const uint32_t id_s = idesc_major(FMT, 128, BKV, 0, 0);
-            const uint32_t id_pv = idesc_major(FMT, 128, a.d, 0, 1);
+            const uint32_t id_pv = idesc_major(FMT, 128, NG * 16, 0, 1);
             const uint64_t dQ = umma_desc(smem_u32(sQ), 2048, 128, kLayoutNone);   // K-major: k-group stride 128 rows x 16 B, 8-row stride 128 B
             // P_i V_i: A = the P tile (K-major over the keys); B[N = dims][K = keys] = the V block read MN-major (8 dims contiguous; the
             // next 8 dims 2048 B on; the next 8 keys 128 B on); 8 k-steps of 16 keys
@@ -125,114 +130,159 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int row = warp * 32 + lane;
         const uint32_t lane_taddr = static_cast<uint32_t>(warp * 32) << 16;
         const float sl = a.scale_log2;
-        const int ng = a.d / 16;            // 16-column groups of an output row
+        constexpr int DR = NG * 16;         // head dim (compile time: the output row lives in registers)
+        constexpr bool ONE_PASS = NG <= 3;  // d <= 48: the whole 128-column score row fits in registers next to the output row
         float m = -INFINITY, l = 0.f;
-        float o[80];
+        float o[DR];
 #pragma unroll
-        for (int i = 0; i < 80; ++i) o[i] = 0.f;
+        for (int i = 0; i < DR; ++i) o[i] = 0.f;
 
+        FA_TRACE(0);
         for (int j = 0; j < a.nblk; ++j) {
             const int sb = j & 1;
             const int valid = min(BKV, a.L - j * BKV);     // keys of this block that exist
             const uint32_t ts = tS + sb * 128 + lane_taddr;
-            mbar_wait_nocall(&bars[B_S_FULL + sb], (j >> 1) & 1);
-            tc_fence_after();
-            // pass 1: the row maximum of the block
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t r[64];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld16(ts + hf * 64 + c * 16, r + c * 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    reg_tie16(r + c * 16);
-                    const int nv = valid - (hf * 64 + c * 16);
-                    if (nv < 16) mask16(r + c * 16, nv);
-                    mx = fmaxf(mx, max16(r + c * 16));
-                }
-            }
-            const float m_new = fmaxf(m, mx * sl);
-            const float alpha = ex2_approx(m - m_new);   // 0 for the first block (m = -inf)
-            // pass 2: P = exp2(s * sl - m_new) -> 16-bit tile (K-major core matrices over the keys), row sum in fp32
-            float sum = 0.f;
             const uint32_t p_row = smem_u32(sP + sb * 32768) + row * 16;
-#pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t r[64];
+            mbar_wait_spin(&bars[B_S_FULL + sb], (j >> 1) & 1);
+            tc_fence_after();
+            if (j < 15) FA_TRACE(1 + j * 4);
+            float m_new, alpha;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pv[DR];
+            if (ONE_PASS) {
+                // the score row: one trip to tensor memory, after which the buffer goes straight back to the MMA thread
+                uint32_t r[128];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld16(ts + hf * 64 + c * 16, r + c * 16);
+                for (int c = 0; c < 8; ++c) tmem_ld16(ts + c * 16, r + c * 16);
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    reg_tie16(r + c * 16);
-                    const int nv = valid - (hf * 64 + c * 16);
-                    if (nv < 16) mask16(r + c * 16, nv);
+                for (int c = 0; c < 8; ++c) reg_tie16(r + c * 16);
+                tc_fence_before();
+                mbar_arrive(&bars[B_S_FREE + sb]);
+                if (valid < BKV) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (valid - c * 16 < 16) mask16(r + c * 16, valid - c * 16);
+                }
+                float mx8[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) mx8[c] = max16(r + c * 16);
+                const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+                m_new = fmaxf(m, mx * sl);
+                alpha = ex2_approx(m - m_new);   // 0 for the first block (m = -inf)
+                if (j < 15) FA_TRACE(2 + j * 4);
+                if (j >= 1) {   // the previous block's P V has long completed: start its trip out of tensor memory under the exp2 pass
+                    const int pb = (j - 1) & 1;
+                    mbar_wait_spin(&bars[B_PV_FULL + pb], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < NG; ++c) tmem_ld16(tPV + pb * 128 + lane_taddr + c * 16, pv + c * 16);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
                     float e[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         e[i] = ex2_approx(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new));
-                        sum += e[i];
+                        sum4[i & 3] += e[i];
                     }
-                    store16<FMT>(p_row + (hf * 8 + c * 2) * 2048, e);
+                    store16<FMT>(p_row + c * 2 * 2048, e);
                 }
+            } else {
+                // two passes over tensor memory (row maximum, then exp2): 64 columns in registers at a time
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t r[64];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld16(ts + hf * 64 + c * 16, r + c * 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        reg_tie16(r + c * 16);
+                        const int nv = valid - (hf * 64 + c * 16);
+                        if (nv < 16) mask16(r + c * 16, nv);
+                        mx = fmaxf(mx, max16(r + c * 16));
+                    }
+                }
+                m_new = fmaxf(m, mx * sl);
+                alpha = ex2_approx(m - m_new);
+                if (j < 15) FA_TRACE(2 + j * 4);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t r[64];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld16(ts + hf * 64 + c * 16, r + c * 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        reg_tie16(r + c * 16);
+                        const int nv = valid - (hf * 64 + c * 16);
+                        if (nv < 16) mask16(r + c * 16, nv);
+                        float e[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            e[i] = ex2_approx(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new));
+                            sum4[i & 3] += e[i];
+                        }
+                        store16<FMT>(p_row + (hf * 8 + c * 2) * 2048, e);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars[B_S_FREE + sb]);        // the score buffer may take block j + 2
             }
-            tc_fence_before();
-            mbar_arrive(&bars[B_S_FREE + sb]);            // the score buffer may take block j + 2
             fence_proxy_async_smem();                     // P tile -> visible to the tensor core
             mbar_arrive(&bars[B_P_FULL + sb]);
-            l = l * alpha + sum;
+            if (j < 15) FA_TRACE(3 + j * 4);
+            l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             // fold in the previous block's P V (it ran while this block's softmax did), then move everything to the new maximum
             if (j >= 1) {
                 const int pb = (j - 1) & 1;
-                mbar_wait_nocall(&bars[B_PV_FULL + pb], ((j - 1) >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tp = tPV + pb * 128 + lane_taddr;
-                uint32_t r[80];
+                if (!ONE_PASS) {
+                    mbar_wait_spin(&bars[B_PV_FULL + pb], ((j - 1) >> 1) & 1);
+                    tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 5; ++c)
-                    if (c < ng) tmem_ld16(tp + c * 16, r + c * 16);
+                    for (int c = 0; c < NG; ++c) tmem_ld16(tPV + pb * 128 + lane_taddr + c * 16, pv + c * 16);
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 5; ++c)
-                    if (c < ng) {
-                        reg_tie16(r + c * 16);
+                for (int c = 0; c < NG; ++c) {
+                    reg_tie16(pv + c * 16);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[c * 16 + i] = (o[c * 16 + i] + __uint_as_float(r[c * 16 + i])) * alpha;
-                    }
+                    for (int i = 0; i < 16; ++i) o[c * 16 + i] = (o[c * 16 + i] + __uint_as_float(pv[c * 16 + i])) * alpha;
+                }
                 tc_fence_before();
                 mbar_arrive(&bars[B_PV_FREE + pb]);
             }
             m = m_new;
+            if (j < 15) FA_TRACE(4 + j * 4);
         }
         {   // the last block's P V, normalisation, store
             const int pb = (a.nblk - 1) & 1;
-            mbar_wait_nocall(&bars[B_PV_FULL + pb], ((a.nblk - 1) >> 1) & 1);
+            mbar_wait_spin(&bars[B_PV_FULL + pb], ((a.nblk - 1) >> 1) & 1);
             tc_fence_after();
             const uint32_t tp = tPV + pb * 128 + lane_taddr;
-            uint32_t r[80];
+            uint32_t r[DR];
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-                if (c < ng) tmem_ld16(tp + c * 16, r + c * 16);
+            for (int c = 0; c < NG; ++c) tmem_ld16(tp + c * 16, r + c * 16);
             tmem_ld_wait();
             const float inv = 1.0f / l;
             const int q = m0 + row;
-            uint16_t* op = a.O + static_cast<int64_t>(b) * a.o_bs + static_cast<int64_t>(q) * a.o_rs + h * a.d;
+            uint16_t* op = a.O + static_cast<int64_t>(b) * a.o_bs + static_cast<int64_t>(q) * a.o_rs + h * DR;
 #pragma unroll
-            for (int c = 0; c < 5; ++c)
-                if (c < ng) {
-                    reg_tie16(r + c * 16);
-                    uint32_t w[8];
+            for (int c = 0; c < NG; ++c) {
+                reg_tie16(r + c * 16);
+                uint32_t w[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        w[i] = pack2<FMT>((o[c * 16 + 2 * i] + __uint_as_float(r[c * 16 + 2 * i])) * inv,
-                                          (o[c * 16 + 2 * i + 1] + __uint_as_float(r[c * 16 + 2 * i + 1])) * inv);
-                    if (q < a.S) {
-                        *reinterpret_cast<uint4*>(op + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4*>(op + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-                    }
+                for (int i = 0; i < 8; ++i)
+                    w[i] = pack2<FMT>((o[c * 16 + 2 * i] + __uint_as_float(r[c * 16 + 2 * i])) * inv,
+                                      (o[c * 16 + 2 * i + 1] + __uint_as_float(r[c * 16 + 2 * i + 1])) * inv);
+                if (q < a.S) {
+                    *reinterpret_cast<uint4*>(op + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(op + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
                 }
+            }
+            FA_TRACE(62);
         }
     }
     tc_fence_before();
@@ -289,10 +339,24 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     rc = make(&tmV, V, v_bs, v_rs, L);
     if (rc) return rc;
 
+    typedef void (*Fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, FaArgs);
+    static const Fn table[2][5] = {
+        {flash_attn_kernel<0, 1>, flash_attn_kernel<0, 2>, flash_attn_kernel<0, 3>, flash_attn_kernel<0, 4>, flash_attn_kernel<0, 5>},
+        {flash_attn_kernel<1, 1>, flash_attn_kernel<1, 2>, flash_attn_kernel<1, 3>, flash_attn_kernel<1, 4>, flash_attn_kernel<1, 5>}};
     static std::atomic<uint64_t> attr_mask{0};
     if (first_use_on_device(attr_mask)) {
-        APX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        APX_CUDA(cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int f = 0; f < 2; ++f)
+            for (int n = 0; n < 5; ++n)
+                APX_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(table[f][n]), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    const Fn fn = table[dtype == APX_F16 ? 0 : 1][d / 16 - 1];
+    static const bool trace_on = [] { const char* e = getenv("APX_FLASH_TRACE"); return e && e[0] == '1'; }();
+    static long long* trace_buf = nullptr;
+    a.trace = nullptr;
+    if (trace_on) {
+        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 64 * sizeof(long long)));
+        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 64 * sizeof(long long), st));
+        a.trace = trace_buf;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ceil_div(S, 128), H, B);
@@ -303,9 +367,19 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     cfg.attrs = attrs;
     cfg.numAttrs = 0;
     add_pdl_attr(attrs, &cfg.numAttrs);
-    if (dtype == APX_F16) APX_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<0>, tmQ, tmK, tmV, a));
-    else                  APX_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<1>, tmQ, tmK, tmV, a));
+    APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmQ, tmK, tmV, a));
     APX_LAUNCH_CHECK("flash_attn_kernel");
+    if (trace_on) {
+        long long t[64];
+        APX_CUDA(cudaStreamSynchronize(st));
+        APX_CUDA(cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost));
+        printf("[apx flash trace] B=%d S=%d L=%d C=%d H=%d (cycles since kernel entry, thread 0 of CTA 0): loop start %lld\n", B, S, L, C, H, t[0] - t[63]);
+        for (int j = 0; j < a.nblk && j < 15; ++j)
+            printf("  block %d: s_seen %lld max_done %lld p_arrived %lld folded %lld\n", j, t[1 + j * 4] - t[63], t[2 + j * 4] - t[63],
+                   t[3 + j * 4] - t[63], t[4 + j * 4] - t[63]);
+        printf("  stored %lld\n", t[62] - t[63]);
+        fflush(stdout);
+    }
     return APX_OK;
 }
 

@@ -52,6 +52,11 @@ int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const ui
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
             int64_t ldr, void* out, int64_t ldo, int M, int N, int K, int in_dtype, int out_dtype, int epilogue,
             cudaStream_t st, const float* ln_c1 = nullptr, float ln_eps = 0.f, void* out2 = nullptr, int64_t ldo2 = 0);
+// flash-style attention over any number of keys (apx_flash_attn.cu)
+bool flash_attn_supported(int C, int H);
+int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t k_bs, int64_t k_rs, const void* V, int64_t v_bs,
+               int64_t v_rs, void* O, int64_t o_bs, int64_t o_rs, int B, int S, int L, int C, int H, int dtype, cudaStream_t st);
+
 // internal epilogue flag: never split K (the context projections: a row's value must not depend on how many rows the call has)
 #define APX_EPI_NOSPLIT 16
 // 16-bit-output specialisation (apx_gemm16.cu); gemm_tc routes to it when gemm16_supported()

@@ -79,8 +79,11 @@ def workload_config(batch: int, n_gpus: int) -> dict:
 HOST_GRAPH = ("adapter sites: libapx (all-heads site kernel at C=256, one-head cluster site kernel at C=384, 3-kernel form at C=640; residual "
               "add folded in); GEGLU FeedForwards: 2 libapx GEMMs with GEGLU / residual epilogues; convolutional trunk channels-last with "
               "libapx GroupNorm(+conv bias + time embedding)+SiLU and ResnetBlock output-add kernels, proj_in / proj_out as linears on the "
-              "token view, one GEMM for all time-embedding projections; plain attention sites: fused QKV projection on cuBLAS + cuDNN SDPA, "
-              "T5 K/V projected once per context; one CUDA graph per step")
+              "token view, one GEMM for all time-embedding projections; LayerNorms folded into the libapx GEMMs (norm3 -> GEGLU projection "
+              "everywhere, norm1 / norm2 -> Q(KV) projection at sites with >= 1000 rows, norm2 -> site kernel at C=256); plain attention "
+              "sites: fused QKV projection (cuBLAS below 1000 rows), self-attention core in libapx (apx_flash_attention) while its grid fits "
+              "one wave, cuDNN SDPA otherwise and at the masked T5 sites, to_out on cuBLAS; T5 K/V projected once per context; one CUDA "
+              "graph per step")
 
 
 def peaks() -> dict:

@@ -19,6 +19,7 @@
  *   apx_linear            the nn.Linear dispatches on the path (attention_processor.py:387,457;
  *                         timm Block qkv/proj/fc1/fc2 used by audio_encoder/models_mae.py:220-231)
  *   apx_attention         F.scaled_dot_product_attention call sites
+ *   apx_flash_attention   the same for long key sequences (the UNet's self-attention sites)
  *                         (attention_processor.py:274,429,443; timm Attention in models_mae.py:566)
  *   apx_audiomae_fwd      audio_encoder/AudioMAE.py:190-212 (forward) -> :37-55 ->
  *                         audio_encoder/models_mae.py:548-570 (encoder) -> AudioMAE.py:148-182 (pool)
@@ -121,6 +122,21 @@ int apx_attention(const void* Q, int64_t q_bs, int64_t q_rs,
                   void* O, int64_t o_bs, int64_t o_rs,
                   int B, int S, int H, int d, int L, int L0, float w0, float w1,
                   int dtype, void* stream);
+
+/*
+ * Plain softmax attention over ANY number of keys (flash-style: keys streamed in blocks of 128, running max / sum in registers) —
+ * the F.scaled_dot_product_attention call of AttnProcessor2_0 (APadapter/ap_adapter/attention_processor.py:267-274) at the
+ * self-attention sites of the UNet (S = L = 1000 / 252 / 64 tokens), no mask:
+ *   O[b,s,h,:] = softmax_l(q·k_l / sqrt(d)) v_l
+ *   Q, O : [B, S, C] views, K, V : [B, L, C] views, C = H*d, element strides (*_bs per batch element, *_rs per row; multiples of 8),
+ *   columns contiguous — the q / k / v column slices of one fused QKV projection are such views.
+ * dtype APX_F16 | APX_BF16.  d % 16 == 0, 16 <= d <= 80 (APX_EUNSUPPORTED otherwise; no fallback).
+ */
+int apx_flash_attention(const void* Q, int64_t q_bs, int64_t q_rs,
+                        const void* K, int64_t k_bs, int64_t k_rs,
+                        const void* V, int64_t v_bs, int64_t v_rs,
+                        void* O, int64_t o_bs, int64_t o_rs,
+                        int B, int S, int L, int C, int H, int dtype, void* stream);
 
 /*
  * Context K/V cache of one adapter site (timestep-invariant; build once per generation).

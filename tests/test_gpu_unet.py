@@ -27,6 +27,13 @@ def _folded_norm_sites(bc=2) -> int:
     return 0 if n <= 0 else sum(14 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if bc * s >= n)   # (adapter sites: no extra launch)
 
 
+def _flash_sites(bc=2, heads=8) -> int:
+    """Self-attention sites whose unmasked SDPA runs in libapx (apx_flash_attention): 8 attn1 sites per attention-bearing resnet layer,
+    at the levels with at least flash_min_keys keys whose grid fits flash_max_ctas."""
+    n, cap = AttnProcessor2_0.flash_min_keys, AttnProcessor2_0.flash_max_ctas
+    return sum(8 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if s >= n and bc * heads * ((s + 127) // 128) <= cap)
+
+
 def _fused_ff_count(unet) -> int:
     with torch.no_grad():
         return sum(m.fused_ok(torch.empty(1, m.net[2].out_features, device="cuda", dtype=torch.float16))
@@ -73,7 +80,7 @@ def test_unet_step_matches_pytorch_processors(setup):
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values())
     assert n_ff == 128 and n_plain == 224
-    assert launched >= _site_launches() + 2 * n_ff + 109 + 22 + _folded_norm_sites(), launched   # + channels-last GroupNorm / output adds, folded norms
+    assert launched >= _site_launches() + 2 * n_ff + 109 + 22 + _folded_norm_sites() + _flash_sites(), launched   # + channels-last GroupNorm / output adds, folded norms
     assert torch.isfinite(y).all()
     # two fp16 evaluations of a 700 M-parameter network that differ only in the 32 adapter sites' rounding
     assert rel_err(y, y_ref) < 1e-2
@@ -95,8 +102,8 @@ def test_cuda_graph_loop_equals_eager_loop(setup):
     # residual GEMM is opt-in, APX_FOLD_RESIDUAL=1)
     n_ff = _fused_ff_count(unet)
     n_plain = sum(isinstance(p, AttnProcessor2_0) for p in ours.values()) if BasicTransformerBlock.fold_residual is True else 0
-    # sites, FeedForwards, channels-last GroupNorms / output adds, Q(KV) projections with a folded LayerNorm
-    assert per_step == _site_launches() + 2 * n_ff + n_plain + 109 + 22 + _folded_norm_sites()
+    # sites, FeedForwards, channels-last GroupNorms / output adds, Q(KV) projections with a folded LayerNorm, self-attention cores
+    assert per_step == _site_launches() + 2 * n_ff + n_plain + 109 + 22 + _folded_norm_sites() + _flash_sites()
     assert _lib.launch_count() - n0 == 3 * per_step
     again = den.denoise(*args, num_inference_steps=200, guidance_scale=7.5, use_cuda_graph=True, steps_to_run=3)
     assert torch.equal(again, graphed)
