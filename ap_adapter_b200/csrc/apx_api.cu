@@ -464,6 +464,7 @@ static int audiomae_encode_into(const float* mel, const apx_vit_weights* w, floa
     } else {
         APX_STEP(apx_patch_embed(mel, w->patch_wT, w->patch_b, w->pos_embed, w->cls_token, x, B, stream));
     }
+    static const bool mae_flash = [] { const char* e = getenv("APX_MAE_FLASH"); return !(e && e[0] == '0'); }();
     for (int l = 0; l < w->depth; ++l) {
         const apx_vit_block& k = w->blocks[l];
         const bool fold = tc && k.qkv_wg && k.qkv_c1 && k.qkv_c2 && k.fc1_wg && k.fc1_c1 && k.fc1_c2;
@@ -477,7 +478,10 @@ static int audiomae_encode_into(const float* mel, const apx_vit_weights* w, floa
         if (!tc)   // CUDA-core cross-check (shared-memory K/V, warp-shuffle softmax)
             APX_STEP(apx_attention(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304,
                                    att, 513LL * 768, 768, B, 513, 12, 64, 513, 513, 1.0f, 0.0f, dt, stream));
-        else       // product path: tcgen05 attention core, N = 513 keys in 128-column chunks
+        else if (mae_flash)   // product path: flash-style tcgen05 attention straight from the q / k / v column slices of the qkv projection
+            APX_STEP(flash_attn(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304, att, 513LL * 768, 768, B,
+                                513, 513, 768, 12, dt, st));
+        else       // APX_MAE_FLASH=0: the round-1 core (K / V re-laid into operand tiles, the whole 513-key score row in tensor memory)
             APX_STEP(attention_tc(qkv, 513LL * 2304, 2304, qkv + 768, 513LL * 2304, 2304, qkv + 1536, 513LL * 2304, 2304, att,
                                   513LL * 768, 768, B, 513, 12, 64, 513, dt, base + ws.tiles, st));
         if (tc) APX_STEP(gemm_tc(att, 768, k.proj_w, 768, k.proj_b, x, 768, x, 768, rows, 768, 768, dt, APX_F32, APX_EPI_NONE, st, nullptr, 0.f,

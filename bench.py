@@ -341,8 +341,9 @@ def audiomae_timing(iters: int = 20) -> dict:
     dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(0)
     enc = AudioMAEConditionCTPoolRand(checkpoint_path=None).to(dev).half().eval()
-    out = {"kernels": "patchify + gemm_tc (patch-embed: bias + pos / CLS residual) + 12 x (gemm_tc qkv with norm1 folded, kv_pack_views + ipattn_core "
-                      "(tcgen05, N=513), gemm_tc proj+res, gemm_tc fc1+GELU with norm2 folded, gemm_tc fc2+res) + layernorm + pool",
+    out = {"kernels": "patchify + gemm16 (patch-embed: bias + pos / CLS residual) + 12 x (gemm16 qkv with norm1 folded, flash_attn (tcgen05, "
+                      "N=513 keys in 128-key blocks, straight from the qkv slices), gemm_tc proj+res, gemm16 fc1+GELU with norm2 folded, "
+                      "gemm_tc fc2+res) + layernorm + pool",
            "flops_per_clip": 97.0e9}
     for b in (1, 8):
         mel = torch.randn(b, 1024, 128, device=dev) * 0.45 - 0.45

@@ -70,7 +70,7 @@ def test_encoder_matches_reference_output_fixture(tag, model, gold):
     mel = cases.make_mel() if tag == "synth" else torch.from_numpy(gold["mel_piano_f16"]).float().unsqueeze(0)
     n0 = _lib.launch_count()
     rep = model.audiomae(mel.unsqueeze(1).cuda(), no_mask=True, no_average=True)
-    assert _lib.launch_count() - n0 >= 3 + 12 * 6 + 1      # patch-embed (weight, patchify, GEMM), 6 kernels per block, final LayerNorm
+    assert _lib.launch_count() - n0 >= 3 + 12 * 5            # patch-embed (weight, patchify, GEMM), 5 kernels per block, final LayerNorm
     assert rep.shape == (1, 513, 768)
     enc_err = rel_err(rep[0, ::8], torch.from_numpy(gold[f"{tag}_encoder_rows"]))
     record(f"audiomae/encoder12_{tag}", err=enc_err, bar=ENC_TOL)

@@ -28,10 +28,11 @@ def _folded_norm_sites(bc=2) -> int:
 
 
 def _flash_sites(bc=2, heads=8) -> int:
-    """Self-attention sites whose unmasked SDPA runs in libapx (apx_flash_attention): 8 attn1 sites per attention-bearing resnet layer,
-    at the levels with at least flash_min_keys keys whose grid fits flash_max_ctas."""
+    """Self-attention sites whose unmasked SDPA runs in libapx (apx_flash_attention): per attention-bearing resnet layer the 8 attn1
+    sites and the 4 attn2 sites without a context (cross_attention_dim None), at the levels with at least flash_min_keys keys whose
+    grid fits flash_max_ctas."""
     n, cap = AttnProcessor2_0.flash_min_keys, AttnProcessor2_0.flash_max_ctas
-    return sum(8 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if s >= n and bc * heads * ((s + 127) // 128) <= cap)
+    return sum(12 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if s >= n and bc * heads * ((s + 127) // 128) <= cap)
 
 
 def _fused_ff_count(unet) -> int:
