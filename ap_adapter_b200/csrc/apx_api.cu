@@ -71,7 +71,8 @@ int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const ui
     }
     const CUtensorMapDataType dt = dtype == APX_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r = fn(tm, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     APX_REQUIRE(r == CUDA_SUCCESS, APX_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
     return APX_OK;

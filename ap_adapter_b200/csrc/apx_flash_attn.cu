@@ -23,7 +23,7 @@
 namespace apx {
 namespace {
 
-constexpr int NT = 192;
+constexpr int NT = 320;      // warps 0-3 / 4-7: softmax warpgroups A / B; warp 8: TMEM + MMA issue; warp 9: TMA
 constexpr int BKV = 128;
 constexpr int MAX_ST = 3;
 
@@ -35,11 +35,14 @@ struct FaArgs {
     float scale_log2;        // log2(e) / sqrt(d)
     uint32_t tile_bytes;     // 128 * d * 2: a Q tile, a K block, a V block
     uint32_t off_k, off_v, off_p, off_bar;
+    int swz;                 // 0: tiles in no-swizzle core-matrix order (4-D maps, 16-byte pieces); 64 / 128: whole 64- / 128-byte rows, TMA-swizzled
     long long* trace;        // diagnostic (APX_FLASH_TRACE=1): clock64 stamps of thread 0 of CTA (0,0,0), 4 per key block
 };
 
 #define FA_TRACE(slot) \
     do { if (a.trace && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.trace[(slot)] = clock64(); } while (0)
+#define FA_TRACE_MMA(slot) \
+    do { if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.trace[(slot)] = clock64(); } while (0)
 
 enum { B_Q = 0, B_KV_FULL = 1, B_KV_FREE = 4, B_S_FULL = 7, B_S_FREE = 9, B_P_FULL = 11, B_PV_FULL = 13, B_PV_FREE = 15, B_COUNT = 17 };
 
@@ -52,8 +55,8 @@ __global__ void __launch_bounds__(NT, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                   FaArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint8_t* sQ = smem;                      // [d/8][128][8]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                      // [d/8][128][8], or [128][d] swizzled
     uint8_t* sK = smem + a.off_k;            // stages x [d/8][128 keys][8]
     uint8_t* sV = smem + a.off_v;            // stages x [d/8][128 keys][8]   (read MN-major as B[N = dims][K = keys])
     uint8_t* sP = smem + a.off_p;            // 2 x [128 keys / 8][128 rows][8]
@@ -64,7 +67,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
 
     FA_TRACE(63);
-    if (threadIdx.x == 160) {
+    if (threadIdx.x == 256) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
@@ -74,7 +77,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc<512>(tmem_slot);
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
     pdl_wait();
     tc_fence_before();
     __syncthreads();
@@ -84,71 +87,103 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // tensor memory: score buffers at columns 0 and 128, P V accumulators at 256 and 384
     const uint32_t tS = tmem_base, tPV = tmem_base + 256;
 
-    if (warp == 5) {
+    if (warp == 9) {
         if (elect_one()) {
             mbar_expect_tx(&bars[B_Q], a.tile_bytes);
-            tma_load_4d(sQ, &tmQ, 0, m0, h * (a.d / 8), b, &bars[B_Q]);
+            if (a.swz) tma_load_3d(sQ, &tmQ, h * a.d, m0, b, &bars[B_Q]);
+            else       tma_load_4d(sQ, &tmQ, 0, m0, h * (a.d / 8), b, &bars[B_Q]);
             for (int j = 0; j < a.nblk; ++j) {
                 const int st = j % a.stages;
                 if (j >= a.stages) mbar_wait(&bars[B_KV_FREE + st], ((j / a.stages) - 1) & 1);
                 mbar_expect_tx(&bars[B_KV_FULL + st], 2 * a.tile_bytes);
-                tma_load_4d(sK + st * a.tile_bytes, &tmK, 0, j * BKV, h * (a.d / 8), b, &bars[B_KV_FULL + st]);
-                tma_load_4d(sV + st * a.tile_bytes, &tmV, 0, j * BKV, h * (a.d / 8), b, &bars[B_KV_FULL + st]);
+                if (a.swz) {
+                    tma_load_3d(sK + st * a.tile_bytes, &tmK, h * a.d, j * BKV, b, &bars[B_KV_FULL + st]);
+                    tma_load_3d(sV + st * a.tile_bytes, &tmV, h * a.d, j * BKV, b, &bars[B_KV_FULL + st]);
+                } else {
+                    tma_load_4d(sK + st * a.tile_bytes, &tmK, 0, j * BKV, h * (a.d / 8), b, &bars[B_KV_FULL + st]);
+                    tma_load_4d(sV + st * a.tile_bytes, &tmV, 0, j * BKV, h * (a.d / 8), b, &bars[B_KV_FULL + st]);
+                }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         if (elect_one()) {
             const uint32_t id_s = idesc_major(FMT, 128, BKV, 0, 0);
             const uint32_t id_pv = idesc_major(FMT, 128, NG * 16, 0, 1);
-            const uint64_t dQ = umma_desc(smem_u32(sQ), 2048, 128, kLayoutNone);   // K-major: k-group stride 128 rows x 16 B, 8-row stride 128 B
+            // Operand tiles.  swz == 0: [d/8][128][8] core matrices — K-major: k-group stride 2048 B, 8-row stride 128 B, a 16-element
+            // k-step is two k-groups; V read MN-major: next 8 keys (K group) 128 B on = "leading" offset, next 8 dims 2048 B on = "stride"
+            // offset.  swz == 64 / 128: [128 rows][d] with rows of 64 / 128 bytes in the TMA swizzle pattern — K-major: 8-row stride
+            // 8 x row bytes, a k-step is 32 B along the row; V read MN-major: the d contiguous elements ARE the swizzle row, the next
+            // 8 keys are 8 rows on ("stride" offset), a 16-key k-step is 16 rows.
+            const uint32_t rowb = static_cast<uint32_t>(a.d) * 2;
+            const uint64_t lay = a.swz == 128 ? kLayoutSW128 : a.swz == 64 ? kLayoutSW64 : kLayoutNone;
+            const uint32_t k_lbo = a.swz ? 16u : 2048u, k_sbo = a.swz ? 8 * rowb : 128u, k_step = a.swz ? 32u : 2 * 2048u;
+            const uint32_t v_lbo = a.swz ? a.tile_bytes : 128u, v_sbo = a.swz ? 8 * rowb : 2048u, v_step = a.swz ? 16 * rowb : 2 * 128u;
+            const uint64_t dQ = umma_desc(smem_u32(sQ), k_lbo, k_sbo, lay);
             // P_i V_i: A = the P tile (K-major over the keys); B[N = dims][K = keys] = the V block read MN-major (8 dims contiguous; the
             // next 8 dims 2048 B on; the next 8 keys 128 B on); 8 k-steps of 16 keys
-            auto issue_pv = [&](int i) {
-                const int pb = i & 1, st = i % a.stages;
-                mbar_wait_spin(&bars[B_P_FULL + pb], (i >> 1) & 1);
-                if (i >= 2) mbar_wait_spin(&bars[B_PV_FREE + pb], ((i >> 1) - 1) & 1);
-                tc_fence_after();
-                mma_chain(tPV + pb * 128, umma_desc(smem_u32(sP + pb * 32768), 2048, 128, kLayoutNone),
-                          umma_desc(smem_u32(sV + st * a.tile_bytes), 128, 2048, kLayoutNone), 2 * 2048, 2 * 128, BKV / 16, id_pv, 0);
-                umma_commit(&bars[B_PV_FULL + pb]);
-                umma_commit(&bars[B_KV_FREE + st]);
-            };
+            // Event-driven issue: the score product of the next block goes out as soon as its K block has landed and its score buffer
+            // has been read (it does not wait behind a P V whose P tile is still being computed), the P V of a block as soon as its P
+            // tile is complete and its accumulator has been folded.  try_wait on a completed phase stays true until this thread acts.
             mbar_wait_spin(&bars[B_Q], 0);
-            for (int j = 0; j < a.nblk; ++j) {
-                const int sb = j & 1, st = j % a.stages;
-                mbar_wait_spin(&bars[B_KV_FULL + st], (j / a.stages) & 1);
-                if (j >= 2) mbar_wait_spin(&bars[B_S_FREE + sb], ((j >> 1) - 1) & 1);
-                tc_fence_after();
-                mma_chain(tS + sb * 128, dQ, umma_desc(smem_u32(sK + st * a.tile_bytes), 2048, 128, kLayoutNone), 2 * 2048, 2 * 2048,
-                          a.d / 16, id_s, 0);
-                umma_commit(&bars[B_S_FULL + sb]);
-                if (j >= 1) issue_pv(j - 1);
+            int js = 0, jp = 0;
+            while (jp < a.nblk) {
+                if (js < a.nblk) {
+                    const int sb = js & 1, st = js % a.stages;
+                    if (mbar_try_wait(&bars[B_KV_FULL + st], (js / a.stages) & 1) &&
+                        (js < 2 || mbar_try_wait(&bars[B_S_FREE + sb], ((js >> 1) - 1) & 1))) {
+                        tc_fence_after();
+                        mma_chain(tS + sb * 128, dQ, umma_desc(smem_u32(sK + st * a.tile_bytes), k_lbo, k_sbo, lay), k_step, k_step, a.d / 16, id_s, 0);
+                        umma_commit(&bars[B_S_FULL + sb]);
+                        if (js < 12) FA_TRACE_MMA(64 + js * 6 + 2);
+                        ++js;
+                    }
+                }
+                if (jp < js) {
+                    const int pb = jp & 1, st = jp % a.stages;
+                    if (mbar_try_wait(&bars[B_P_FULL + pb], (jp >> 1) & 1) && (jp < 2 || mbar_try_wait(&bars[B_PV_FREE + pb], ((jp >> 1) - 1) & 1))) {
+                        tc_fence_after();
+                        // P V: A = the P tile (K-major over the keys), B = the V block read MN-major, 8 k-steps of 16 keys
+                        mma_chain(tPV + pb * 128, umma_desc(smem_u32(sP + pb * 32768), 2048, 128, kLayoutNone),
+                                  umma_desc(smem_u32(sV + st * a.tile_bytes), v_lbo, v_sbo, lay), 2 * 2048, v_step, BKV / 16, id_pv, 0);
+                        umma_commit(&bars[B_PV_FULL + pb]);
+                        umma_commit(&bars[B_KV_FREE + st]);
+                        if (jp < 12) FA_TRACE_MMA(64 + jp * 6 + 4);
+                        ++jp;
+                    }
+                }
             }
-            issue_pv(a.nblk - 1);
         }
     } else {
-        const int row = warp * 32 + lane;
-        const uint32_t lane_taddr = static_cast<uint32_t>(warp * 32) << 16;
+        // ---- softmax warpgroups.  Warpgroup g owns the key blocks j = g, g + 2, ... with its OWN running (m, l, O): block j's score
+        // buffer, P tile and P V accumulator are all indexed by j & 1 = g, so the two warpgroups never synchronise inside the loop — one
+        // computes exp2 (MUFU-bound) while the other waits on tensor memory / folds its P V — and their partial results are merged once.
+        const int g = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_taddr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const float sl = a.scale_log2;
         constexpr int DR = NG * 16;         // head dim (compile time: the output row lives in registers)
-        constexpr bool ONE_PASS = NG <= 3;  // d <= 48: the whole 128-column score row fits in registers next to the output row
+        constexpr bool ONE_PASS = false;    // (the one-trip variant needs ~210 registers: over the 168 a 320-thread CTA gets — kept for a setmaxnreg build)
         float m = -INFINITY, l = 0.f;
         float o[DR];
 #pragma unroll
         for (int i = 0; i < DR; ++i) o[i] = 0.f;
+        const uint32_t ts = tS + g * 128 + lane_taddr;
+        const uint32_t tp = tPV + g * 128 + lane_taddr;
+        const uint32_t p_row = smem_u32(sP + g * 32768) + row * 16;
 
+        // The exp2 passes of the two warpgroups take turns (named barriers 2 / 3 as a token): run at the same time they only split
+        // the MUFU pipe between them and then idle together; alternating, one warpgroup's row maxima / P V fold / barrier waits hide
+        // behind the other's exp2 pass.
+        if (g == 1) named_bar_arrive(2, 256);
         FA_TRACE(0);
-        for (int j = 0; j < a.nblk; ++j) {
-            const int sb = j & 1;
+        int it = 0;                         // how many blocks this warpgroup has processed: barrier phases
+        for (int j = g; j < a.nblk; j += 2, ++it) {
             const int valid = min(BKV, a.L - j * BKV);     // keys of this block that exist
-            const uint32_t ts = tS + sb * 128 + lane_taddr;
-            const uint32_t p_row = smem_u32(sP + sb * 32768) + row * 16;
-            mbar_wait_spin(&bars[B_S_FULL + sb], (j >> 1) & 1);
+            mbar_wait_spin(&bars[B_S_FULL + g], it & 1);
             tc_fence_after();
-            if (j < 15) FA_TRACE(1 + j * 4);
+            if (it < 15) FA_TRACE(1 + it * 4);
             float m_new, alpha;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t pv[DR];
             if (ONE_PASS) {
                 // the score row: one trip to tensor memory, after which the buffer goes straight back to the MMA thread
                 uint32_t r[128];
@@ -158,7 +193,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) reg_tie16(r + c * 16);
                 tc_fence_before();
-                mbar_arrive(&bars[B_S_FREE + sb]);
+                mbar_arrive(&bars[B_S_FREE + g]);
                 if (valid < BKV) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -170,14 +205,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
                 m_new = fmaxf(m, mx * sl);
                 alpha = ex2_approx(m - m_new);   // 0 for the first block (m = -inf)
-                if (j < 15) FA_TRACE(2 + j * 4);
-                if (j >= 1) {   // the previous block's P V has long completed: start its trip out of tensor memory under the exp2 pass
-                    const int pb = (j - 1) & 1;
-                    mbar_wait_spin(&bars[B_PV_FULL + pb], ((j - 1) >> 1) & 1);
+                if (it < 15) FA_TRACE(2 + it * 4);
+                uint32_t pv[DR];
+                if (it >= 1) {   // this warpgroup's previous P V has long completed: start its trip out of tensor memory under the exp2 pass
+                    mbar_wait_spin(&bars[B_PV_FULL + g], (it - 1) & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < NG; ++c) tmem_ld16(tPV + pb * 128 + lane_taddr + c * 16, pv + c * 16);
+                    for (int c = 0; c < NG; ++c) tmem_ld16(tp + c * 16, pv + c * 16);
                 }
+                named_bar_sync(2 + g, 256);               // my turn on the MUFU pipe
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float e[16];
@@ -187,6 +223,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         sum4[i & 3] += e[i];
                     }
                     store16<FMT>(p_row + c * 2 * 2048, e);
+                }
+                named_bar_arrive(3 - g, 256);             // the other warpgroup's turn
+                fence_proxy_async_smem();                     // P tile -> visible to the tensor core
+                mbar_arrive(&bars[B_P_FULL + g]);
+                if (it < 15) FA_TRACE(3 + it * 4);
+                if (it >= 1) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NG; ++c) {
+                        reg_tie16(pv + c * 16);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[c * 16 + i] = (o[c * 16 + i] + __uint_as_float(pv[c * 16 + i])) * alpha;
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bars[B_PV_FREE + g]);
                 }
             } else {
                 // two passes over tensor memory (row maximum, then exp2): 64 columns in registers at a time
@@ -207,7 +258,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
                 m_new = fmaxf(m, mx * sl);
                 alpha = ex2_approx(m - m_new);
-                if (j < 15) FA_TRACE(2 + j * 4);
+                if (it < 15) FA_TRACE(2 + it * 4);
+                if (it >= 1) {   // fold in this warpgroup's previous P V (16 columns at a time): it has also finished reading the P tile
+                    mbar_wait_spin(&bars[B_PV_FULL + g], (it - 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < NG; ++c) {
+                        uint32_t pv[16];
+                        tmem_ld16(tp + c * 16, pv);
+                        tmem_ld_wait16(pv);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[c * 16 + i] = (o[c * 16 + i] + __uint_as_float(pv[i])) * alpha;
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bars[B_PV_FREE + g]);
+                }
+                named_bar_sync(2 + g, 256);               // my turn on the MUFU pipe
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t r[64];
@@ -228,55 +294,55 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         store16<FMT>(p_row + (hf * 8 + c * 2) * 2048, e);
                     }
                 }
+                named_bar_arrive(3 - g, 256);             // the other warpgroup's turn
                 tc_fence_before();
-                mbar_arrive(&bars[B_S_FREE + sb]);        // the score buffer may take block j + 2
+                mbar_arrive(&bars[B_S_FREE + g]);         // the score buffer may take this warpgroup's next block
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[B_P_FULL + g]);
+                if (it < 15) FA_TRACE(3 + it * 4);
             }
-            fence_proxy_async_smem();                     // P tile -> visible to the tensor core
-            mbar_arrive(&bars[B_P_FULL + sb]);
-            if (j < 15) FA_TRACE(3 + j * 4);
             l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
-            // fold in the previous block's P V (it ran while this block's softmax did), then move everything to the new maximum
-            if (j >= 1) {
-                const int pb = (j - 1) & 1;
-                if (!ONE_PASS) {
-                    mbar_wait_spin(&bars[B_PV_FULL + pb], ((j - 1) >> 1) & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < NG; ++c) tmem_ld16(tPV + pb * 128 + lane_taddr + c * 16, pv + c * 16);
-                }
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < NG; ++c) {
-                    reg_tie16(pv + c * 16);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) o[c * 16 + i] = (o[c * 16 + i] + __uint_as_float(pv[c * 16 + i])) * alpha;
-                }
-                tc_fence_before();
-                mbar_arrive(&bars[B_PV_FREE + pb]);
-            }
             m = m_new;
-            if (j < 15) FA_TRACE(4 + j * 4);
+            if (it < 15) FA_TRACE(4 + it * 4);
         }
-        {   // the last block's P V, normalisation, store
-            const int pb = (a.nblk - 1) & 1;
-            mbar_wait_spin(&bars[B_PV_FULL + pb], ((a.nblk - 1) >> 1) & 1);
+        if ((a.nblk & 1) == g) named_bar_sync(2 + g, 256);   // the token's last hand-over has no taker: consume it (barriers end balanced)
+        if (it >= 1) {   // this warpgroup's last P V
+            mbar_wait_spin(&bars[B_PV_FULL + g], (it - 1) & 1);
             tc_fence_after();
-            const uint32_t tp = tPV + pb * 128 + lane_taddr;
-            uint32_t r[DR];
 #pragma unroll
-            for (int c = 0; c < NG; ++c) tmem_ld16(tp + c * 16, r + c * 16);
-            tmem_ld_wait();
-            const float inv = 1.0f / l;
+            for (int c = 0; c < NG; ++c) {
+                uint32_t pv[16];
+                tmem_ld16(tp + c * 16, pv);
+                tmem_ld_wait16(pv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[c * 16 + i] += __uint_as_float(pv[i]);
+            }
+        }
+        // ---- merge: warpgroup B hands (m, l, O) of every row to warpgroup A through the (now dead) P tiles
+        float* xch = reinterpret_cast<float*>(sP) + row;     // [2 + DR][128] floats, column = row: conflict-free
+        named_bar_sync(1, 256);                               // both warpgroups have seen their last P V: no MMA reads the P tiles any more
+        if (g == 1) {
+            xch[0] = m;
+            xch[128] = l;
+#pragma unroll
+            for (int i = 0; i < DR; ++i) xch[(2 + i) * 128] = o[i];
+        }
+        named_bar_sync(1, 256);
+        if (g == 0) {
+            const float mb = xch[0], lb = xch[128];
+            const float mm = fmaxf(m, mb);
+            const float fa = ex2_approx(m - mm), fb = ex2_approx(mb - mm);   // warpgroup B without blocks: mb = -inf -> fb = 0
+            const float inv = 1.0f / (l * fa + lb * fb);
             const int q = m0 + row;
             uint16_t* op = a.O + static_cast<int64_t>(b) * a.o_bs + static_cast<int64_t>(q) * a.o_rs + h * DR;
 #pragma unroll
             for (int c = 0; c < NG; ++c) {
-                reg_tie16(r + c * 16);
                 uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    w[i] = pack2<FMT>((o[c * 16 + 2 * i] + __uint_as_float(r[c * 16 + 2 * i])) * inv,
-                                      (o[c * 16 + 2 * i + 1] + __uint_as_float(r[c * 16 + 2 * i + 1])) * inv);
+                for (int i = 0; i < 8; ++i) {
+                    const int e0 = c * 16 + 2 * i;
+                    w[i] = pack2<FMT>((o[e0] * fa + xch[(2 + e0) * 128] * fb) * inv, (o[e0 + 1] * fa + xch[(3 + e0) * 128] * fb) * inv);
+                }
                 if (q < a.S) {
                     *reinterpret_cast<uint4*>(op + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(op + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -287,7 +353,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<512>(tmem_base);
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
@@ -321,7 +387,9 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     a.off_v = a.off_k + a.stages * a.tile_bytes;
     a.off_p = a.off_v + a.stages * a.tile_bytes;
     a.off_bar = a.off_p + 2 * 32768;
-    const size_t smem = 128 + a.off_bar + B_COUNT * 8 + 16;
+    static const bool swz_off = [] { const char* e = getenv("APX_FLASH_SWIZZLE"); return e && e[0] == '0'; }();
+    a.swz = swz_off ? 0 : d == 32 ? 64 : d == 64 ? 128 : 0;   // head rows of exactly one swizzle span
+    const size_t smem = 1024 + a.off_bar + B_COUNT * 8 + 16;
     APX_REQUIRE(smem <= 227 * 1024, APX_EUNSUPPORTED, "flash_attn: %zu B of shared memory", smem);
 
     CUtensorMap tmQ, tmK, tmV;
@@ -330,6 +398,12 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
         uint64_t dims[4] = {8, static_cast<uint64_t>(rows), static_cast<uint64_t>(C / 8), static_cast<uint64_t>(B)};
         uint64_t strides[3] = {static_cast<uint64_t>(rs) * 2, 16, static_cast<uint64_t>(bs) * 2};
         uint32_t box[4] = {8, 128, static_cast<uint32_t>(d / 8), 1};
+        if (a.swz) {   // [B][rows][C]: the box {d, 128, 1} lands as 128 rows of d elements in the TMA swizzle pattern
+            uint64_t dims3[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(rows), static_cast<uint64_t>(B)};
+            uint64_t strides3[2] = {static_cast<uint64_t>(rs) * 2, static_cast<uint64_t>(bs) * 2};
+            uint32_t box3[3] = {static_cast<uint32_t>(d), 128, 1};
+            return encode_tmap(tm, dtype, 3, p, dims3, strides3, box3, a.swz == 128 ? 1 : 2);
+        }
         return encode_tmap(tm, dtype, 4, p, dims, strides, box, 0);
     };
     int rc = make(&tmQ, Q, q_bs, q_rs, S);
@@ -354,8 +428,8 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     static long long* trace_buf = nullptr;
     a.trace = nullptr;
     if (trace_on) {
-        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 64 * sizeof(long long)));
-        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 64 * sizeof(long long), st));
+        if (!trace_buf) APX_CUDA(cudaMalloc(&trace_buf, 160 * sizeof(long long)));
+        APX_CUDA(cudaMemsetAsync(trace_buf, 0, 160 * sizeof(long long), st));
         a.trace = trace_buf;
     }
     cudaLaunchConfig_t cfg = {};
@@ -370,7 +444,7 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     APX_CUDA(cudaLaunchKernelEx(&cfg, fn, tmQ, tmK, tmV, a));
     APX_LAUNCH_CHECK("flash_attn_kernel");
     if (trace_on) {
-        long long t[64];
+        long long t[160];
         APX_CUDA(cudaStreamSynchronize(st));
         APX_CUDA(cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost));
         printf("[apx flash trace] B=%d S=%d L=%d C=%d H=%d (cycles since kernel entry, thread 0 of CTA 0): loop start %lld\n", B, S, L, C, H, t[0] - t[63]);
@@ -378,6 +452,9 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
             printf("  block %d: s_seen %lld max_done %lld p_arrived %lld folded %lld\n", j, t[1 + j * 4] - t[63], t[2 + j * 4] - t[63],
                    t[3 + j * 4] - t[63], t[4 + j * 4] - t[63]);
         printf("  stored %lld\n", t[62] - t[63]);
+        for (int j = 0; j < a.nblk && j < 12; ++j)
+            printf("  mma block %d: kv_full %lld s_free %lld s_issued %lld | p_full %lld pv_free %lld\n", j, t[64 + j * 6] - t[63], t[64 + j * 6 + 1] - t[63],
+                   t[64 + j * 6 + 2] - t[63], t[64 + j * 6 + 3] - t[63], t[64 + j * 6 + 4] - t[63]);
         fflush(stdout);
     }
     return APX_OK;

@@ -46,7 +46,8 @@ static inline int    elem_size(int dtype) { return dtype == APX_F32 ? 4 : 2; }
 
 // ---- TMA descriptor encoding (driver entry point resolved at run time; no -lcuda) ------
 int encode_tmap(CUtensorMap* tm, int dtype, int rank, const void* base, const uint64_t* dims,
-                const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle128);
+                const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
+                int swizzle128 /* 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_64B */);
 
 // ---- tcgen05 kernels --------------------------------------------------------------------
 int gemm_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
