@@ -57,9 +57,12 @@ class AttnProcessor2_0(nn.Module):
     # torch's cuDNN SDPA; APX_FLASH_ATTN=0 disables, APX_FLASH_ATTN=n sets the threshold
     flash_min_keys = (lambda v: 1 << 30 if v == "0" else int(v))(os.environ.get("APX_FLASH_ATTN", "200"))
     # ... and only while its grid (one CTA per 128-query tile, head and batch element) fits one wave of the 148 SMs: measured on B200,
-    # 13.7 vs 14.2 us (cuDNN) at B = 2, S = 1000, C = 256 and 6.4 vs 6.8 us at S = 252, C = 384, but 92 vs 49 us at B = 16 (one
-    # 227-register CTA per SM: nothing overlaps its latencies once there is more than one wave)
+    # 11.3 vs 14.5 us (cuDNN) at B = 2, S = 1000, C = 256, but 76 vs 49 us at B = 16 (one CTA per SM with 232-register softmax
+    # threads: once there is more than one wave cuDNN's kernel wins)
     flash_max_ctas = int(os.environ.get("APX_FLASH_MAX_CTAS", "160"))
+    # ... and for the head sizes whose rows are exactly one TMA swizzle span (64 / 128 bytes: whole-row Q / K / V loads; at d = 48 the
+    # 16-byte-piece tile loads leave it at 7.3 us against cuDNN's 6.9 at S = 252)
+    flash_head_dims = (32, 64)
 
     def __init__(self, hidden_size=None, cross_attention_dim=None):
         super().__init__()
@@ -177,7 +180,7 @@ class AttnProcessor2_0(nn.Module):
         head_dim = key.shape[-1] // attn.heads
         if (attention_mask is None and query.is_cuda and not torch.is_grad_enabled() and key.shape[1] >= self.flash_min_keys
                 and batch_size * attn.heads * ((query.shape[1] + 127) // 128) <= self.flash_max_ctas and query.dtype in (torch.float16, torch.bfloat16) and query.dim() == 3 and key.dtype == query.dtype
-                and _lib.flash_attention_ok(key.shape[-1], attn.heads) and query.stride(2) == 1 and key.stride(2) == 1
+                and head_dim in self.flash_head_dims and query.stride(2) == 1 and key.stride(2) == 1
                 and value.stride(2) == 1):
             # the unmasked SDPA (reference :267-274) in libapx: keys streamed through tcgen05 in blocks of 128, straight from the
             # (possibly strided) q / k / v slices of the fused projection; the output is already token-major [B, S, C]

@@ -23,9 +23,12 @@
 namespace apx {
 namespace {
 
-constexpr int NT = 320;      // warps 0-3 / 4-7: softmax warpgroups A / B; warp 8: TMEM + MMA issue; warp 9: TMA
+constexpr int NT = 384;      // warps 0-3 / 4-7: softmax warpgroups A / B; warp 8: TMEM + MMA issue; warp 9: TMA; warps 10-11 idle (they complete
+                             // the third warpgroup so that setmaxnreg can move its registers to the softmax warpgroups)
+constexpr int REGS_WG = 232; // setmaxnreg: (232 - 168) * 256 registers claimed = (168 - 40) * 128 released; the kernel must not contain a call
+constexpr int REGS_AUX = 40;
 constexpr int BKV = 128;
-constexpr int MAX_ST = 3;
+constexpr int MAX_ST = 5;     // K / V ring: deep enough that a block's loads start two blocks before its scores are wanted
 
 struct FaArgs {
     uint16_t* O;
@@ -44,7 +47,7 @@ struct FaArgs {
 #define FA_TRACE_MMA(slot) \
     do { if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.trace[(slot)] = clock64(); } while (0)
 
-enum { B_Q = 0, B_KV_FULL = 1, B_KV_FREE = 4, B_S_FULL = 7, B_S_FREE = 9, B_P_FULL = 11, B_PV_FULL = 13, B_PV_FREE = 15, B_COUNT = 17 };
+enum { B_Q = 0, B_KV_FULL = 1, B_KV_FREE = 6, B_S_FULL = 11, B_S_FREE = 13, B_P_FULL = 15, B_PV_FULL = 17, B_PV_FREE = 19, B_COUNT = 21 };
 
 __device__ __forceinline__ uint32_t idesc_major(int fmt, int M, int N, int a_mn, int b_mn) {
     return umma_idesc_f16(fmt, M, N) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16);
@@ -87,6 +90,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // tensor memory: score buffers at columns 0 and 128, P V accumulators at 256 and 384
     const uint32_t tS = tmem_base, tPV = tmem_base + 256;
 
+    if (warp >= 8) {   // the register re-balancing must dominate each role's code: one branch per register budget
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     if (warp == 9) {
         if (elect_one()) {
             mbar_expect_tx(&bars[B_Q], a.tile_bytes);
@@ -94,7 +99,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             else       tma_load_4d(sQ, &tmQ, 0, m0, h * (a.d / 8), b, &bars[B_Q]);
             for (int j = 0; j < a.nblk; ++j) {
                 const int st = j % a.stages;
-                if (j >= a.stages) mbar_wait(&bars[B_KV_FREE + st], ((j / a.stages) - 1) & 1);
+                if (j >= a.stages) mbar_wait_nocall(&bars[B_KV_FREE + st], ((j / a.stages) - 1) & 1);
                 mbar_expect_tx(&bars[B_KV_FULL + st], 2 * a.tile_bytes);
                 if (a.swz) {
                     tma_load_3d(sK + st * a.tile_bytes, &tmK, h * a.d, j * BKV, b, &bars[B_KV_FULL + st]);
@@ -153,7 +158,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
+    }   // warps 10, 11: idle
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WG));
         // ---- softmax warpgroups.  Warpgroup g owns the key blocks j = g, g + 2, ... with its OWN running (m, l, O): block j's score
         // buffer, P tile and P V accumulator are all indexed by j & 1 = g, so the two warpgroups never synchronise inside the loop — one
         // computes exp2 (MUFU-bound) while the other waits on tensor memory / folds its P V — and their partial results are merged once.
@@ -162,7 +169,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t lane_taddr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const float sl = a.scale_log2;
         constexpr int DR = NG * 16;         // head dim (compile time: the output row lives in registers)
-        constexpr bool ONE_PASS = false;    // (the one-trip variant needs ~210 registers: over the 168 a 320-thread CTA gets — kept for a setmaxnreg build)
+        constexpr bool ONE_PASS = NG <= 2;  // d <= 32: the whole 128-column score row fits in the 232 registers next to the output row
         float m = -INFINITY, l = 0.f;
         float o[DR];
 #pragma unroll
@@ -332,7 +339,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const float mb = xch[0], lb = xch[128];
             const float mm = fmaxf(m, mb);
             const float fa = ex2_approx(m - mm), fb = ex2_approx(mb - mm);   // warpgroup B without blocks: mb = -inf -> fb = 0
-            const float inv = 1.0f / (l * fa + lb * fb);
+            const float inv = __fdividef(1.0f, l * fa + lb * fb);   // (a precise division would bring a call into a setmaxnreg kernel)
             const int q = m0 + row;
             uint16_t* op = a.O + static_cast<int64_t>(b) * a.o_bs + static_cast<int64_t>(q) * a.o_rs + h * DR;
 #pragma unroll
@@ -382,7 +389,7 @@ int flash_attn(const void* Q, int64_t q_bs, int64_t q_rs, const void* K, int64_t
     a.nblk = ceil_div(L, BKV);
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(d));
     a.tile_bytes = 128u * d * 2;
-    a.stages = std::min(a.nblk, MAX_ST);
+    a.stages = std::min(a.nblk, std::min(MAX_ST, static_cast<int>((220 * 1024 - a.tile_bytes - 2 * 32768) / (2 * a.tile_bytes))));
     a.off_k = a.tile_bytes;
     a.off_v = a.off_k + a.stages * a.tile_bytes;
     a.off_p = a.off_v + a.stages * a.tile_bytes;

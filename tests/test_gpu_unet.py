@@ -32,7 +32,8 @@ def _flash_sites(bc=2, heads=8) -> int:
     sites and the 4 attn2 sites without a context (cross_attention_dim None), at the levels with at least flash_min_keys keys whose
     grid fits flash_max_ctas."""
     n, cap = AttnProcessor2_0.flash_min_keys, AttnProcessor2_0.flash_max_ctas
-    return sum(12 * layers for layers, s in ((5, 1000), (5, 252), (6, 64)) if s >= n and bc * heads * ((s + 127) // 128) <= cap)
+    dims = AttnProcessor2_0.flash_head_dims
+    return sum(12 * layers for layers, s, d in ((5, 1000, 32), (5, 252, 48), (6, 64, 80)) if s >= n and d in dims and bc * heads * ((s + 127) // 128) <= cap)
 
 
 def _fused_ff_count(unet) -> int:
