@@ -725,11 +725,13 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
     from ap_adapter_b200.attention_processor import AttnProcessor2_0
     from ap_adapter_b200.pipeline import APAdapterDenoiser
     from ap_adapter_b200.unet import NHWC, BasicTransformerBlock, FeedForward, build_attn_processors
-    saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled, AttnProcessor2_0.cache_context)
+    saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled, AttnProcessor2_0.cache_context,
+             AttnProcessor2_0.flash_min_keys)
     dev = lat0.device
     try:
         FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
         AttnProcessor2_0.cache_context = False
+        AttnProcessor2_0.flash_min_keys = 1 << 30     # the stock graph keeps torch's SDPA everywhere
         theirs = build_attn_processors(unet, _TorchIPAttnSite, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
         for k, p in ours.items():
             if hasattr(p, "to_k_ip"):
@@ -762,7 +764,7 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
                         "unfused FeedForward / projections / residual adds, one CUDA graph per step, device-timed"}
     finally:
         (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled,
-         AttnProcessor2_0.cache_context) = saved
+         AttnProcessor2_0.cache_context, AttnProcessor2_0.flash_min_keys) = saved
         unet.set_attn_processor(dict(ours))
 
 
