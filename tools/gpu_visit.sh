@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit (run under gpurun from the repo root):  tools/gpu_visit.sh TAG [steps...]
-#   steps: smoke tests ubench harness bench bench8 ncu_site launches profile    (default: smoke tests bench)
+#   steps: smoke tests testsall ubench harness bench bench8 ncu_site ncu_all launches profile    (default: smoke tests bench)
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2}; shift || true
@@ -26,6 +26,13 @@ for s in $STEPS; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/launches_${TAG}.csv \
           python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_${TAG}.log 2>&1
       wc -l gpurun_out/launches_${TAG}.csv ;;
+    ncu_all)
+      echo "== ncu full, every libapx kernel once (tools/ncu_kernels.py); the report stays on the box, the raw page comes back"
+      timeout 1500 ncu --set full --clock-control none -k regex:'gemm|ipattn|flash|groupnorm|add_bias|kv_pack|layernorm|pool_tokens|patchify|fbank|wave_mean|resample|wgrad' \
+          -o /tmp/prof_${TAG}_all -f python tools/ncu_kernels.py > gpurun_out/ncu_${TAG}_all.log 2>&1
+      ncu -i /tmp/prof_${TAG}_all.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_all_raw.csv 2>/dev/null
+      python tools/ncu_summary.py gpurun_out/prof_${TAG}_all_raw.csv > gpurun_out/ncu_${TAG}_all_kernels.txt; gzip -f gpurun_out/prof_${TAG}_all_raw.csv
+      head -70 gpurun_out/ncu_${TAG}_all_kernels.txt | cut -c1-200 ;;
     profile) echo "== step profile"; PYTHONPATH=. timeout 600 python tools/profile_step.py > gpurun_out/step_profile_${TAG}.txt 2>&1; head -40 gpurun_out/step_profile_${TAG}.txt ;;
     *) echo "unknown step $s" ;;
   esac

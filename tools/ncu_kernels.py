@@ -21,7 +21,7 @@ lib = _lib.load()
 # audio front-end: polyphase resample (44.1 kHz -> 16 kHz, 160 phases) + batched Kaldi fbank, 4 clips of 10 s
 wav = torch.randn(4, 441000, device=dev) * 0.1
 extract_kaldi_fbank_feature_batch(wav, 44100, 1024)
-# AudioMAE encode + pool, 8 clips (patchify, gemm_tc<64/128> incl. folded LayerNorm, kv_pack_views, ipattn_core, layernorm, pool_tokens)
+# AudioMAE encode + pool, 8 clips (patchify, gemm16 / gemm_tc incl. folded LayerNorm, flash_attn, layernorm, pool_tokens)
 os.environ["APX_MAE_GRAPH"] = "0"
 from ap_adapter_b200.audiomae import MaskedAutoencoderViTEncoder  # noqa: E402
 MaskedAutoencoderViTEncoder.use_graph = False
@@ -60,5 +60,20 @@ for variant, (bc, s, c) in ((_lib.APX_SITE_ONEHEAD, (2, 64, 640)), (_lib.APX_SIT
     with torch.no_grad():
         proc(attn, case["x"].to(dev, torch.float16), encoder_hidden_states=case["ctx"].to(dev, torch.float16))
     lib.apx_set_site_variant(_lib.APX_SITE_AUTO)
+# flash-style self-attention: the UNet's S = 1000 sites (d = 32, one wave / batch 8) and the ViT's 513 keys (d = 64)
+for (b, s, c, h) in ((2, 1000, 256, 8), (16, 1000, 256, 8), (8, 513, 768, 12)):
+    qkv = torch.randn(b, s, 3 * c, device=dev, dtype=torch.float16)
+    q, k, v = qkv.chunk(3, dim=-1)
+    _lib.flash_attention(q, k, v, h)
+# the token GEMMs of one denoise step through apx_gemm16 (direct TMA-store epilogue / cluster split-K finisher)
+for (m, n, k, kind) in ((2000, 768, 256, "ln"), (504, 384, 1536, "res"), (128, 640, 2560, "res"), (128, 5120, 640, "ln_geglu"), (2000, 256, 256, "res")):
+    a = torch.randn(m, k, device=dev, dtype=torch.float16)
+    w = torch.randn(n, k, device=dev, dtype=torch.float16) * 0.05
+    b16 = torch.randn(n, device=dev, dtype=torch.float16)
+    if kind.startswith("ln"):
+        wg, c1, c2 = _lib.fold_layernorm(w, b16, torch.ones(k, device=dev, dtype=torch.float16), torch.zeros(k, device=dev, dtype=torch.float16))
+        _lib.linear_lnfold(a, wg, c1, c2, 1e-5, geglu=kind.endswith("geglu"))
+    else:
+        _lib.linear(a, w, b16.float(), residual=torch.randn(m, n, device=dev, dtype=torch.float16))
 torch.cuda.synchronize()
 print("done")
