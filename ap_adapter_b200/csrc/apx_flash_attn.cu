@@ -72,6 +72,34 @@ __device__ __forceinline__ float ex2_poly(float x) {
     p = fmaf(p, f, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(y) << 23));
 }
+// Packed fp32 pairs (FFMA2 / FADD2 on sm_100): the exp2 pass is bound by issue slots, and these halve the scale-and-shift and the
+// row-sum instructions around the MUFU operations.
+__device__ __forceinline__ void fma2(float& y0, float& y1, float x0, float x1, float s, float c) {
+    uint64_t xx, ss, cc, rr;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(xx), "l"(ss), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(rr));
+}
+__device__ __forceinline__ void add2(uint64_t& acc, float a, float b) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
+}
+// 16 scores -> exp2(s * sl - m) in e[], accumulated into two packed partial sums
+__device__ __forceinline__ void exp16(const uint32_t* r, float sl, float neg_m, float* e, uint64_t& acc0, uint64_t& acc1) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        float t0, t1;
+        fma2(t0, t1, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), sl, neg_m);
+        e[i] = ex2_approx(t0);
+        e[i + 1] = ex2_approx(t1);
+        if (i & 2) add2(acc1, e[i], e[i + 1]);
+        else       add2(acc0, e[i], e[i + 1]);
+    }
+}
+
 template <int POLY_EVERY>
 __device__ __forceinline__ float ex2_mixed(float x, int i) {   // i: compile-time element index
     return (POLY_EVERY > 0 && (i % (POLY_EVERY > 0 ? POLY_EVERY : 1)) == (POLY_EVERY > 0 ? POLY_EVERY : 1) - 1) ? ex2_poly(x) : ex2_approx(x);
@@ -216,6 +244,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (it < 15) FA_TRACE(1 + it * 4);
             float m_new, alpha;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint64_t acc0 = 0, acc1 = 0;            // two packed pairs of partial row sums
             if (ONE_PASS) {
                 // the score row: one trip to tensor memory, after which the buffer goes straight back to the MMA thread
                 uint32_t r[128];
@@ -249,10 +278,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float e[16];
+                    if (POLY_EVERY == 0) {
+                        exp16(r + c * 16, sl, -m_new, e, acc0, acc1);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        e[i] = ex2_mixed<POLY_EVERY>(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new), i);
-                        sum4[i & 3] += e[i];
+                        for (int i = 0; i < 16; ++i) {
+                            e[i] = ex2_mixed<POLY_EVERY>(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new), i);
+                            sum4[i & 3] += e[i];
+                        }
                     }
                     store16<FMT>(p_row + c * 2 * 2048, e);
                 }
@@ -318,10 +351,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         const int nv = valid - (hf * 64 + c * 16);
                         if (nv < 16) mask16(r + c * 16, nv);
                         float e[16];
+                        if (POLY_EVERY == 0) {
+                            exp16(r + c * 16, sl, -m_new, e, acc0, acc1);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            e[i] = ex2_mixed<POLY_EVERY>(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new), i);
-                            sum4[i & 3] += e[i];
+                            for (int i = 0; i < 16; ++i) {
+                                e[i] = ex2_mixed<POLY_EVERY>(fmaf(__uint_as_float(r[c * 16 + i]), sl, -m_new), i);
+                                sum4[i & 3] += e[i];
+                            }
                         }
                         store16<FMT>(p_row + (hf * 8 + c * 2) * 2048, e);
                     }
@@ -333,7 +370,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_arrive(&bars[B_P_FULL + g]);
                 if (it < 15) FA_TRACE(3 + it * 4);
             }
-            l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+            {
+                float a0, a1, a2, a3;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc0));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(acc1));
+                l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) + ((a0 + a1) + (a2 + a3));
+            }
             m = m_new;
             if (it < 15) FA_TRACE(4 + it * 4);
         }
