@@ -181,7 +181,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             // next 8 dims 2048 B on; the next 8 keys 128 B on); 8 k-steps of 16 keys
             // Event-driven issue: the score product of the next block goes out as soon as its K block has landed and its score buffer
             // has been read (it does not wait behind a P V whose P tile is still being computed), the P V of a block as soon as its P
-            // tile is complete and its accumulator has been folded.  try_wait on a completed phase stays true until this thread acts.
+            // tile is complete and its accumulator has been folded.  try_wait on a completed phase stays true until this thread acts
+            // (the non-blocking mbarrier.test_wait measured the same here: profiles/r2w_flash_poll_ab.txt).
             mbar_wait_spin(&bars[B_Q], 0);
             int js = 0, jp = 0;
             while (jp < a.nblk) {

@@ -12,9 +12,11 @@
 //             X chunks (SWIZZLE_128B tensor TMA) and packed Wq chunks (1-D bulk TMA) through a 2-stage mbarrier ring;
 //             both warpgroups convert the fp32 accumulator to the 16-bit K-major operand tile sQO (all heads side by side).
 //   phase B   heads alternate between two softmax warpgroups (WG0: 0,2,4.. WG1: 1,3,5..), each with its own S / O_t / O_a
-//             accumulators in tensor memory and its own P tile in shared memory.  The single MMA thread keeps
-//             S(h+2) = Q_h+2 K^T and O(h) = P V in flight while the other warpgroup is in its exp2 pass, so the MUFU
-//             pipe — the real bound of this kernel at d = 32 (one ex2 per score, 16/clk/SM) — stays busy.
+//             accumulators in tensor memory and its own P tile in shared memory.  The single MMA thread issues event-driven
+//             (two in-order queues, S and P·V, polled with mbarrier.test_wait): S(h+2) goes out as soon as its warpgroup has
+//             moved S(h) to registers, P·V(h) as soon as P(h) is stored; the exp2 passes of the two warpgroups take turns
+//             (named-barrier token), so the MUFU pipe — the real bound of this kernel at d = 32 (one ex2 per score, 16/clk/SM)
+//             — is fed by one warpgroup while the other loads scores, takes maxima and converts its previous head's output.
 //             O_h = O_t / l_t + ap_scale · O_a / l_a is formed in registers and written over Q_h in sQO.
 //   phase C   Y[128, C] = O[128, H*d_pad] · Wo^T as C-wide MMAs over the gathered O tile (Wo chunks stream through the
 //             shared memory the P tiles occupied), + bias, 16-bit, swizzled staging tile, tensor-TMA store (rows past S clipped).
@@ -64,7 +66,8 @@ constexpr int X_CHUNK_BYTES = 128 * 64 * 2;   // one SWIZZLE_128B box: 128 rows 
 constexpr int WO_KSTEPS_PER_STAGE = 4;
 constexpr int NTHREADS = 384;          // 3 warpgroups: two softmax warpgroups + {MMA warp, TMA warp, two idle warps}
 constexpr int REGS_WG = 216;           // setmaxnreg: the softmax warpgroups keep a 144-column score row in registers,
-constexpr int REGS_AUX = 72;           // the single-thread roles give their registers up (registers freed: (168-72)*128 = registers claimed: (216-168)*256)
+constexpr int REGS_AUX = 72;           // the single-thread roles give theirs up: (168 - 72) * 128 freed = (216 - 168) * 256 claimed
+                                       // (224 / 56 and 232 / 40 measured no faster: profiles/r2r_site_ab.txt)
 
 // Per cluster size cs (G = Nq / cs rows of Wq, cn = C / cs columns of Wo per CTA):
 // WQ section: [cs][C/64][8][G][8]: element (rank r, chunk kb, k-group kg, row n, e) = Wq[h*d + j, kb*64 + kg*8 + e] with
@@ -123,6 +126,8 @@ struct SiteArgs {
     long long* trace;                          // diagnostic (APX_SITE_TRACE=1): clock64 stamps of CTA (0,0)
 };
 
+
+
 // trace slots: [0,32) MMA thread, [32,64) producer, [64,192) WG0 thread 0 (8 per head), [192,320) WG1 thread 128
 #define SITE_T(slot)                                                                             \
     do {                                                                                         \
@@ -134,6 +139,35 @@ enum {  // mbarrier slots (40 x 8 bytes reserved; the TMEM slot and the bias sli
     B_S_FREE = 24, B_P_FULL = 26, B_O_FULL = 28, B_PV_ALL = 30, B_SO_ALL = 31, B_Y = 32, B_OALL = 33, B_DONE = 34, B_STAT = 35, B_COUNT = 36
 };
 constexpr uint32_t BAR_REGION_BYTES = 384;   // barriers [0, 320) | TMEM slot at 320 | bias slice from 384 | folded-LayerNorm c1, c2 behind it
+
+// O_h = O_t / l_t + ap_scale * O_a / l_a -> 16 bit, over Q_h in sQO (dst = this thread's row of head h's slot); l_t, l_a = accumulator
+// column d_pad (the ones row of the V^T tile).  One 16-column group of each accumulator per round trip: with two, the 64 staging
+// registers next to the 144-register score row spilled to local memory inside the head loop (-1.2 us per call at Bc = 16).
+template <int FMT>
+__device__ __forceinline__ void site_convert_head(const SiteArgs& a, uint32_t tOt, uint32_t tOa, uint32_t dst) {
+    uint32_t lt, la;
+    tmem_ld1(tOt + a.d_pad, lt);
+    tmem_ld1(tOa + a.d_pad, la);
+    float w_t = 0.f, w_a = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < a.d_pad; c0 += 16) {
+        uint32_t rt[16], ra[16];
+        tmem_ld16(tOt + c0, rt);
+        tmem_ld16(tOa + c0, ra);
+        tmem_ld_wait();
+        if (c0 == 0) {
+            asm volatile("" : "+r"(lt), "+r"(la) : : "memory");
+            w_t = a.Lt > 0 ? __fdividef(1.0f, __uint_as_float(lt)) : 0.f;
+            w_a = a.La > 0 ? __fdividef(a.ap_scale, __uint_as_float(la)) : 0.f;
+        }
+        reg_tie16(rt);
+        reg_tie16(ra);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ra[i]), w_a, __uint_as_float(rt[i]) * w_t);
+        store16<FMT>(dst + c0 / 8 * 2048, v);
+    }
+}
 
 // N16 > 0: the score row is N16 16-column groups, the first LT16 of them text, and it is read from tensor memory ONCE and kept
 //          in registers for both softmax passes (the score buffer is handed back to the MMA thread right after the load).
@@ -283,9 +317,9 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             }
             umma_commit(&bars[B_Q]);
             SITE_T(2);
-            // ---- phase B.  Per pair of heads (one per warpgroup): as soon as a warpgroup has moved its score row to registers
-            //      (S_FREE) the scores of its NEXT head are issued, so they are complete long before it needs them; P·V of a head
-            //      is issued when its P tile is ready (P_FULL) and runs under the other warpgroup's / the next head's softmax.
+            // ---- phase B.  As soon as a warpgroup has moved its score row to registers (S_FREE) the scores of its NEXT head are
+            //      issued, so they are complete long before it needs them; P·V of a head is issued when its P tile is ready
+            //      (P_FULL) and runs under the other warpgroup's / the next head's softmax.
             const uint64_t dQO = umma_desc(smem_u32(sQO), 2048, 128, kLayoutNone);
             const uint32_t head_bytes = (a.d_pad / 8) * 2048;   // one head's slice of sQO
             const uint32_t idesc_v = umma_idesc_f16(FMT, 128, a.dv_pad);
@@ -297,45 +331,48 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mbar_wait_nocall(&bars[B_SQ], 0);   // every Q column is in sQO; the Q accumulator columns are free
             tc_fence_after();
             SITE_T(3);
-            const int n_pairs = (a.hg + 1) / 2;
-#pragma unroll 1
-            for (int p = 0; p <= n_pairs; ++p) {
-                const uint32_t par = (p - 1) & 1;
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {   // scores of heads 2p, 2p+1
-                    const int h = 2 * p + g;   // local head index; global head = h_first + h
-                    if (h >= a.hg) break;
-                    if (p > 0) {   // S(h - 2) is in registers: its buffer is free
-                        mbar_wait_nocall(&bars[B_S_FREE + g], par);
-                        tc_fence_after();
+            {
+                // Event-driven issue (as in apx_flash_attn.cu): two in-order queues — the scores of head hs go out as soon as their K
+                // tile has landed and warpgroup hs & 1 has moved its previous score row to registers; the P·V of head hp as soon as
+                // its P tile is complete.  Neither queue waits behind the other, so one warpgroup's P·V is never held up by the
+                // other warpgroup's score buffer (round 1 issued S(2p), S(2p+1), PV(2p-2), PV(2p-1) in order with blocking waits, which
+                // pulled the warpgroups into lockstep: -0.5 us per call at Bc = 2, profiles/r2q_site_ab.txt).  test_wait, not try_wait:
+                // try_wait may park the thread when the phase is incomplete, and this thread polls several barriers.
+                int hs = 0, hp = 0;
+                uint32_t polls = 0;
+                while (hp < a.hg) {
+                    if (++polls > (1u << 26)) asm volatile("trap;");   // a protocol bug becomes a CUDA error, not a hung GPU
+                    if (hs < a.hg) {
+                        const int g = hs & 1;
+                        if (mbar_test_wait(&bars[B_K_FULL + sk], pk) && (hs < 2 || mbar_test_wait(&bars[B_S_FREE + g], ((hs >> 1) - 1) & 1))) {
+                            tc_fence_after();
+                            mma_chain(tmem_base + g * a.L_pad, desc_add(dQO, (h_first + hs) * head_bytes), desc_add(dK0, sk * a.k_tile_bytes),
+                                      2 * 2048, 2 * a.L_pad * 16, a.d_pad / 16, idesc_s, 0);
+                            umma_commit(&bars[B_S_FULL + g]);
+                            umma_commit(&bars[B_K_EMPTY + sk]);
+                            if (++sk == a.nk) { sk = 0; pk ^= 1; }
+                            ++hs;
+                            polls = 0;
+                        }
                     }
-                    mbar_wait_nocall(&bars[B_K_FULL + sk], pk);
-                    tc_fence_after();
-                    mma_chain(tmem_base + g * a.L_pad, desc_add(dQO, (h_first + h) * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048,
-                              2 * a.L_pad * 16, a.d_pad / 16, idesc_s, 0);
-                    umma_commit(&bars[B_S_FULL + g]);
-                    umma_commit(&bars[B_K_EMPTY + sk]);
-                    if (++sk == a.nk) { sk = 0; pk ^= 1; }
-                }
-                if (p == 0) continue;
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {   // P·V of heads 2p-2, 2p-1
-                    const int h = 2 * (p - 1) + g;
-                    if (h >= a.hg) break;
-                    mbar_wait_nocall(&bars[B_P_FULL + g], par);   // P(h) is in shared memory, O(g) has been read
-                    mbar_wait_nocall(&bars[B_V_FULL + sv], pv);
-                    tc_fence_after();
-                    if (h < 8) SITE_T(8 + 2 * h);
-                    const uint64_t dP = desc_add(dP0, g * a.p_bytes), dV = desc_add(dV0, sv * a.v_tile_bytes);
-                    const uint32_t tO = tmem_O + g * 2 * a.dv_pad;
-                    // text columns [0, Lt_pad) -> O_t, audio columns [Lt_pad, L_pad) -> O_a
-                    mma_chain(tO, dP, dV, 2 * 2048, 2 * a.dv_pad * 16, a.Lt_pad / 16, idesc_v, 0);
-                    mma_chain(tO + a.dv_pad, desc_add(dP, (a.Lt_pad / 8) * 2048), desc_add(dV, (a.Lt_pad / 8) * (a.dv_pad * 16)),
-                              2 * 2048, 2 * a.dv_pad * 16, a.La_pad / 16, idesc_v, 0);
-                    umma_commit(&bars[B_O_FULL + g]);
-                    umma_commit(&bars[B_V_EMPTY + sv]);
-                    if (++sv == a.nv) { sv = 0; pv ^= 1; }
-                    if (h < 8) SITE_T(9 + 2 * h);
+                    if (hp < hs) {
+                        const int g = hp & 1;
+                        if (mbar_test_wait(&bars[B_P_FULL + g], (hp >> 1) & 1) && mbar_test_wait(&bars[B_V_FULL + sv], pv)) {
+                            tc_fence_after();
+                            if (hp < 8) SITE_T(8 + 2 * hp);
+                            const uint64_t dP = desc_add(dP0, g * a.p_bytes), dV = desc_add(dV0, sv * a.v_tile_bytes);
+                            const uint32_t tO = tmem_O + g * 2 * a.dv_pad;
+                            mma_chain(tO, dP, dV, 2 * 2048, 2 * a.dv_pad * 16, a.Lt_pad / 16, idesc_v, 0);
+                            mma_chain(tO + a.dv_pad, desc_add(dP, (a.Lt_pad / 8) * 2048), desc_add(dV, (a.Lt_pad / 8) * (a.dv_pad * 16)),
+                                      2 * 2048, 2 * a.dv_pad * 16, a.La_pad / 16, idesc_v, 0);
+                            umma_commit(&bars[B_O_FULL + g]);
+                            umma_commit(&bars[B_V_EMPTY + sv]);
+                            if (++sv == a.nv) { sv = 0; pv ^= 1; }
+                            if (hp < 8) SITE_T(9 + 2 * hp);
+                            ++hp;
+                            polls = 0;
+                        }
+                    }
                 }
             }
             umma_commit(&bars[B_PV_ALL]);
@@ -435,16 +472,18 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             tc_fence_after();
             if (a.cs > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // phase-A stages are dead here
             if (t0) SITE_T(tb + 121);
+            // A compact loop (two 16-column groups per round trip): this code runs ONCE per CTA, so what it costs is mostly its
+            // instruction fetch — the 8-group unrolled form below is 10 KB of straight-line code (measured: 1400-1900 cycles cold).
 #pragma unroll 1
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {   // 8 loads per tcgen05.wait::ld: the round trip is the cost, not the bytes
-                uint32_t r[128];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < c_hi) tmem_ld16(tmem_base + lane_taddr + (c0 + j) * 16, r + j * 16);
+            for (int c0 = c_lo; c0 < c_hi; c0 += 2) {
+                uint32_t r[32];
+                const bool two = c0 + 1 < c_hi;
+                tmem_ld16(tmem_base + lane_taddr + c0 * 16, r);
+                if (two) tmem_ld16(tmem_base + lane_taddr + (c0 + 1) * 16, r + 16);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < c_hi) {
+                for (int j = 0; j < 2; ++j)
+                    if (j == 0 || two) {
                         reg_tie16(r + j * 16);
                         if (a.ln_c1) {   // q = rstd (x Wq'^T - mean c1) + c2
                             const float* c1p = sLn + (h_first * a.d_pad) + (c0 + j) * 16;
@@ -472,38 +511,11 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // O_h = O_t / l_t + ap_scale * O_a / l_a -> 16 bit, over Q_h in sQO; l_t, l_a = accumulator column d_pad (ones row of V^T).
         // A segment that does not exist reads the other accumulator with weight 0 (its own columns were never written).
         const uint32_t tOt = a.Lt > 0 ? tO : tO + a.dv_pad, tOa = a.La > 0 ? tO + a.dv_pad : tO;
-        auto convert_o = [&](int h, uint32_t ph) {
+        auto convert_o = [&](int h, uint32_t ph, int tslot) {
             mbar_wait_nocall(&bars[B_O_FULL + g], ph);
             tc_fence_after();
-            uint32_t lt, la;
-            tmem_ld1(tOt + a.d_pad, lt);
-            tmem_ld1(tOa + a.d_pad, la);
-            float w_t = 0.f, w_a = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < a.d_pad; c0 += 32) {   // two 16-column groups of each accumulator per round trip
-                uint32_t rt[32], ra[32];
-                const bool two = c0 + 16 < a.d_pad;
-                tmem_ld16(tOt + c0, rt);
-                tmem_ld16(tOa + c0, ra);
-                if (two) { tmem_ld16(tOt + c0 + 16, rt + 16); tmem_ld16(tOa + c0 + 16, ra + 16); }
-                tmem_ld_wait();
-                if (c0 == 0) {
-                    asm volatile("" : "+r"(lt), "+r"(la) : : "memory");
-                    w_t = a.Lt > 0 ? 1.0f / __uint_as_float(lt) : 0.f;
-                    w_a = a.La > 0 ? a.ap_scale / __uint_as_float(la) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j == 0 || two) {
-                        reg_tie16(rt + j * 16);
-                        reg_tie16(ra + j * 16);
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(ra[j * 16 + i]), w_a, __uint_as_float(rt[j * 16 + i]) * w_t);
-                        store16<FMT>(sQO_row + ((h_first + h) * a.d_pad + c0 + j * 16) / 8 * 2048, v);
-                    }
-                }
-            }
+            if (tslot >= 0) SITE_T(tslot);
+            site_convert_head<FMT>(a, tOt, tOa, sQO_row + ((h_first + h) * a.d_pad) / 8 * 2048);
             if (a.cs > 1) {
                 // all-gather of the O slices over distributed shared memory, head by head: push this head's slice into every
                 // peer's sQO as soon as it exists; each copy completes its bytes on the peer's B_OALL barrier
@@ -518,7 +530,12 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 }
             }
         };
-        if (g == 1 && a.hg > 2) named_bar_sync(2, 256);
+        // The exp2 passes of the two warpgroups take turns (named barriers 7 / 8 are the token: "warpgroup 0 / 1 may use the MUFU
+        // pipe"): run at the same time they only split the pipe and then idle together; alternating, one warpgroup's score load,
+        // maxima, O conversion and barrier waits hide behind the other's exp2 pass.  Every arrive has a taker (barriers end balanced).
+        // With one head per warpgroup (clusters of 4) there is nothing to hide behind: both go at once.
+        const bool tok = a.hg > 2;
+        if (tok && g == 1) named_bar_arrive(7, 256);
         bool cl_waited = false;
 #pragma unroll 1
         for (int it = 0;; ++it) {
@@ -570,13 +587,11 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
                     cl_waited = true;
                 }
-                convert_o(h - 2, (it - 1) & 1);
+                convert_o(h - 2, (it - 1) & 1, tr ? ts + 5 : -1);
             }
             if (!live) break;
             if (tr) SITE_T(ts + 4);
-            // One-time skew: warpgroup 1 starts when warpgroup 0 enters its first exponential pass, so that from then on one
-            // warpgroup's MUFU-bound pass runs under the other's tensor-memory / conversion work instead of both in lockstep.
-            if (it == 0 && g == 0 && a.hg > 2) named_bar_arrive(2, 256);
+            if (tok) named_bar_sync(7 + g, 256);
             const float mxs_t = mx_t * sl, mxs_a = mx_a * sl;
             if (N16 > 0) {
 #pragma unroll
@@ -594,6 +609,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(&bars[B_S_FREE + g]);
             }
+            if (tok && h + 1 < a.hg) named_bar_arrive(8 - g, 256);   // the other warpgroup's turn
             if (tr) SITE_T(ts + 7);
             fence_proxy_async_smem();
             tc_fence_before();
@@ -847,7 +863,7 @@ int ipattn_site(const void* X, const void* wpack, const void* cache_tiles, const
                 printf("  wg%d : q_wait %lld q_seen %lld sq_arrived %lld | y_wait %lld y_seen %lld staged %lld stored %lld\n", g, rel(o + 120),
                        rel(o + 121), rel(o + 122), rel(o + 123), rel(o + 124), rel(o + 125), rel(o + 126));
                 for (int i = 0; g + 2 * i < H && i < 15; ++i)
-                    printf("  wg%d h%d: top %lld s_seen %lld ld_done %lld max_done %lld oprev_done %lld exp_done %lld p_arrived %lld (unused %lld)\n", g,
+                    printf("  wg%d h%d: top %lld s_seen %lld ld_done %lld max_done %lld oprev_done %lld exp_done %lld p_arrived %lld (o_full_seen %lld)\n", g,
                            g + 2 * i, rel(o + i * 8), rel(o + i * 8 + 1), rel(o + i * 8 + 6), rel(o + i * 8 + 2), rel(o + i * 8 + 4),
                            rel(o + i * 8 + 7), rel(o + i * 8 + 3), rel(o + i * 8 + 5));
             }

@@ -52,6 +52,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may park the thread for a system-dependent time when the phase is incomplete: wrong for a thread that
+// polls SEVERAL barriers and acts on whichever completes first).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.  The failure path is
 // out of line: these kernels are latency-bound single-warp-per-scheduler code and must stay inside the instruction cache.
 static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {

@@ -101,13 +101,21 @@ def cpu_reference(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
     AttnProcessor2_0 at every site (the reference itself is pure Python on diffusers, which this image lacks)."""
     from ap_adapter_b200.pipeline import APAdapterDenoiser
     from ap_adapter_b200.unet import AudioLDM2UNet2DConditionModel, build_attn_processors
+    from oracle import ref_shims
     from oracle.ref_processors import OracleAttnProcessor2_0, OracleIPAttnProcessor2_0
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     unet = AudioLDM2UNet2DConditionModel().eval()
-    unet.set_attn_processor(build_attn_processors(unet, OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, ap_scale=AP_SCALE))
+    if ref_shims.reference_processors_available():
+        # oracle/_ref: the reference's OWN IPAttnProcessor2_0 / AttnProcessor2_0 classes (unmodified attention_processor.py) at the
+        # 256 sites; only the UNet around them is the restated host graph (diffusers is absent from this image)
+        ap = ref_shims.load_attention_processor()
+        ip_cls, plain_cls, procs = ap.IPAttnProcessor2_0, ap.AttnProcessor2_0, "reference classes (oracle/_ref)"
+    else:
+        ip_cls, plain_cls, procs = OracleIPAttnProcessor2_0, OracleAttnProcessor2_0, "oracle port (oracle/ref_processors.py)"
+    unet.set_attn_processor(build_attn_processors(unet, ip_cls, plain_cls, ap_scale=AP_SCALE))
     den = APAdapterDenoiser(unet)
     g = torch.Generator().manual_seed(1)
     lat = torch.randn(batch, *LAT_SHAPE, generator=g)
@@ -134,7 +142,7 @@ def cpu_reference(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
             i += 1
     assert torch.isfinite(lat).all()
     total = sum(times)
-    return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port", "processors": procs,
             "sample": f"{len(times)} full fp32 UNet denoise steps of the same workload (B={batch}) after {i - len(times)} warm-up, "
                       f"torch {torch.__version__} with {torch.get_num_threads()} threads",
             "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times)}
@@ -801,7 +809,7 @@ def run_reference(args) -> dict:
             "dtype": "f32", "data": "synthetic (random-init UNet / adapter weights, N(0,1) latents and contexts)",
             "config": dict(workload_config(args.batch, n), host_arm=f"one host process runs all {args.batch * n} clip(s) of the {n}-GPU job"),
             "impl": "reference",
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "processors", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
 

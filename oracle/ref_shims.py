@@ -18,8 +18,25 @@ import torch.nn as nn
 REF_ROOT = os.environ.get("APX_REFERENCE_ROOT", "/root/reference")
 
 
+REF_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py puts the processor module here
+
+
 def reference_available() -> bool:
+    """The whole reference tree is mounted (this container; never the GPU box)."""
     return os.path.isfile(os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py"))
+
+
+def processor_module_path() -> str | None:
+    """The reference's attention_processor.py: from the mounted tree, else the unmodified copy under oracle/_ref."""
+    for path in (os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py"),
+                 os.path.join(REF_BUILT, "attention_processor.py")):
+        if os.path.isfile(path):
+            return path
+    return None
+
+
+def reference_processors_available() -> bool:
+    return processor_module_path() is not None
 
 
 def _load(name: str, path: str):
@@ -32,7 +49,10 @@ def _load(name: str, path: str):
 
 def load_attention_processor():
     """The reference's attention_processor module (IPAttnProcessor2_0, AttnProcessor2_0, ...)."""
-    return _load("apx_ref_attention_processor", os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py"))
+    path = processor_module_path()
+    if path is None:
+        raise FileNotFoundError("neither /root/reference nor oracle/_ref holds attention_processor.py (run oracle/build_ref.py)")
+    return sys.modules.get("apx_ref_attention_processor") or _load("apx_ref_attention_processor", path)
 
 
 class StubAttention(nn.Module):

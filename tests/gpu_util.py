@@ -69,6 +69,22 @@ def oracle_site(case: dict, dtype, scale=None) -> torch.Tensor:
                                         case["heads"], case["num_tokens"], case["scale"] if scale is None else scale)
 
 
+def reference_class_site(case: dict, dtype, scale=None) -> torch.Tensor:
+    """The reference's own IPAttnProcessor2_0 (oracle/_ref or /root/reference, unmodified) in fp32 on the CPU, fed the operands
+    rounded to `dtype` — what `oracle_site` restates, without the restatement."""
+    ap = ref_shims.load_attention_processor()
+    hidden = case["wq"].shape[0]
+    attn = ref_shims.StubAttention(hidden, cases.DCTX, case["heads"])
+    proc = ap.IPAttnProcessor2_0(hidden_size=hidden, name="ref", cross_attention_dim=cases.DCTX, num_tokens=case["num_tokens"],
+                                 scale=case["scale"] if scale is None else scale)
+    r = lambda k: rounded(case[k], dtype)  # noqa: E731
+    with torch.no_grad():
+        attn.to_q.weight.copy_(r("wq")); attn.to_k.weight.copy_(r("wk")); attn.to_v.weight.copy_(r("wv"))
+        attn.to_out[0].weight.copy_(r("wo")); attn.to_out[0].bias.copy_(r("bo"))
+        proc.to_k_ip.weight.copy_(r("wk_ip")); proc.to_v_ip.weight.copy_(r("wv_ip"))
+        return proc(attn, r("x"), encoder_hidden_states=r("ctx"))
+
+
 def torch_lowp_site(case: dict, dtype, scale=None, device="cuda") -> torch.Tensor:
     """The reference algorithm (attention_processor.py:387-459) run by stock PyTorch ops in `dtype` on the GPU — nn.Linear
     + F.scaled_dot_product_attention, i.e. what the reference's own fp16 inference path computes.  Its distance to the

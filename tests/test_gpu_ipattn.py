@@ -9,7 +9,8 @@ import torch
 from ap_adapter_b200 import _lib
 from oracle import cases
 
-from gpu_util import TOL, build_site, oracle_site, random_site_case, record, rel_err, site_within_bar, torch_lowp_site
+from gpu_util import TOL, build_site, oracle_site, random_site_case, record, reference_class_site, rel_err, rounded, site_within_bar, torch_lowp_site
+from oracle import ref_shims
 
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float16, torch.bfloat16]
@@ -52,6 +53,29 @@ def test_site_matches_oracle(name, dtype):
     else:
         ok, errs = site_within_bar(y, case, dtype, "site_oracle/" + name)
         assert ok, errs
+
+
+@pytest.mark.skipif(not ref_shims.reference_processors_available(), reason="oracle/_ref not built (oracle/build_ref.py)")
+@pytest.mark.parametrize("name", ["cfg1", "site256_real", "site384", "site640"])
+def test_site_matches_the_reference_class_itself(name):
+    """libapx against the reference's OWN IPAttnProcessor2_0 class (oracle/_ref: the unmodified attention_processor.py), run in
+    fp32 on the CPU of this box on the same fp16-rounded operands — no restatement in between.  Bar: the north star's 1e-3
+    (the real-weight site is held to the stock fp16 path's own distance, as in test_site_matches_oracle)."""
+    if name not in cases.IPATTN_CASES:
+        pytest.skip(f"no case {name}")
+    case = cases.make_ipattn_case(name)
+    y = run_site(case, torch.float16)
+    ref = reference_class_site(case, torch.float16)
+    err = rel_err(y, ref)
+    err_port = rel_err(oracle_site(case, torch.float16), ref)   # the restatement against the class it restates, same inputs
+    record("site_reference_class/" + name, dtype="f16", err=err, port_vs_class=err_port)
+    assert err_port < 1e-5, err_port
+    if name == "site256_real":
+        with torch.no_grad():
+            err_torch = rel_err(torch_lowp_site(case, torch.float16), ref)
+        assert err < max(1e-3, 1.1 * err_torch), (err, err_torch)
+    else:
+        assert err < TOL[torch.float16], err
 
 
 @pytest.mark.parametrize("name", list(cases.IPATTN_CASES))

@@ -146,7 +146,7 @@ def test_unet_shapes_follow_the_reference_geometry(tiny_unet):
     assert sorted(set(seen)) == [(64, 128, 768), (252, 96, 768), (1000, 64, 768)]
 
 
-@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present")
+@pytest.mark.skipif(not ref_shims.reference_processors_available(), reason="neither /root/reference nor oracle/_ref present")
 def test_reference_processors_drop_into_the_restated_unet(tiny_unet):
     """The reference's OWN IPAttnProcessor2_0 / AttnProcessor2_0, registered exactly as inference.py:22-59 does, run inside
     the restated host graph and agree with the oracle processors: the duck-typed Attention exposes what they read."""

@@ -84,7 +84,7 @@ def test_audiomae_forward_returns_embedding_and_ones(mae_sd):
     assert emb.shape == (1, 8, 768) and ones.shape == (1, 8) and bool((ones == 1).all())
 
 
-@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not ref_shims.reference_processors_available(), reason="neither /root/reference nor oracle/_ref present")
 def test_oracle_against_live_reference_processor():
     """When the reference tree is mounted, run it live on a fresh seed (not only the committed fixtures)."""
     ap = ref_shims.load_attention_processor()
