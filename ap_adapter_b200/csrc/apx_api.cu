@@ -279,7 +279,13 @@ static int pick_site_kernel(int Bc, int S, int C, int H, int Lt, int La) {
     const H1Geom g = h1_geom(C, H);
     const int tiles = ceil_div(S, 128) * Bc;
     const size_t gather = static_cast<size_t>(H - 1) * g.d_pad * 256;
-    return (tiles * H <= 32 && gather <= 90 * 1024) ? 2 : 0;
+    // Round 2, second half: with the gemm16 epilogues the three-kernel form reads FASTER than the one-head kernel at C = 384 when the
+    // calls run back to back (S = 252, Bc = 2: 16.0 vs 18.5 us at La = 128, profiles/r2x_harness.txt), but inside the denoise step the
+    // two choices give the same step time (8.734 vs 8.735 ms, profiles/r2z_bench_h1max{384,320}.json: three launches behind PyTorch
+    // kernels do not overlap the way back-to-back replays do) — so the single fused kernel stays the choice there.  C = 640 stays on
+    // three kernels (25 vs 15 us).  APX_SITE_H1_MAXC moves the width limit.
+    static const int h1_max_c = [] { const char* e = getenv("APX_SITE_H1_MAXC"); return e ? atoi(e) : 384; }();
+    return (tiles * H <= 32 && gather <= 90 * 1024 && C <= h1_max_c) ? 2 : 0;
 }
 
 size_t apx_ipattn_pack_bytes(int C, int H) {

@@ -183,44 +183,43 @@ ipattn_site4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait_spin(&bars[B_SQ], 0);   // every Q column is in sQO; the Q accumulator columns are free
                 tc_fence_after();
                 S4_T(3);
-                const int n_pairs = (a.H + 1) / 2;
-#pragma unroll 1
-                for (int p = 0; p <= n_pairs; ++p) {
-                    const uint32_t par = (p - 1) & 1;
-#pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {   // scores of heads 2p, 2p+1
-                        const int h = 2 * p + g;
-                        if (h >= a.H) break;
-                        if (p > 0) {   // S(h - 2) is in registers: its buffer is free
-                            mbar_wait_spin(&bars[B_S_FREE + g], par);
-                            tc_fence_after();
+                // Event-driven issue (as in apx_ipattn_site.cu): two in-order queues, polled without blocking
+                {
+                    int hs = 0, hp = 0;
+                    uint32_t polls = 0;
+                    while (hp < a.H) {
+                        if (++polls > (1u << 26)) asm volatile("trap;");   // a protocol bug becomes a CUDA error, not a hung GPU
+                        if (hs < a.H) {
+                            const int g = hs & 1;
+                            if (mbar_test_wait(&bars[B_K_FULL + sk], pk) && (hs < 2 || mbar_test_wait(&bars[B_S_FREE + g], ((hs >> 1) - 1) & 1))) {
+                                tc_fence_after();
+                                mma_chain(tmem_base + g * L_PAD, desc_add(dQO, hs * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048,
+                                          2 * L_PAD * 16, a.d_pad / 16, idesc_s, 0);
+                                umma_commit(&bars[B_S_FULL + g]);
+                                umma_commit(&bars[B_K_EMPTY + sk]);
+                                if (++sk == a.nk) { sk = 0; pk ^= 1; }
+                                ++hs;
+                                polls = 0;
+                            }
                         }
-                        mbar_wait_spin(&bars[B_K_FULL + sk], pk);
-                        tc_fence_after();
-                        mma_chain(tmem_base + g * L_PAD, desc_add(dQO, h * head_bytes), desc_add(dK0, sk * a.k_tile_bytes), 2 * 2048, 2 * L_PAD * 16,
-                                  a.d_pad / 16, idesc_s, 0);
-                        umma_commit(&bars[B_S_FULL + g]);
-                        umma_commit(&bars[B_K_EMPTY + sk]);
-                        if (++sk == a.nk) { sk = 0; pk ^= 1; }
-                    }
-                    if (p == 0) continue;
-#pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {   // P·V of heads 2p-2, 2p-1
-                        const int h = 2 * (p - 1) + g;
-                        if (h >= a.H) break;
-                        mbar_wait_spin(&bars[B_P_FULL + g], par);   // P(h) is in shared memory, O(g) has been read
-                        mbar_wait_spin(&bars[B_V_FULL + sv], pv);
-                        tc_fence_after();
-                        if (h < 8) S4_T(8 + 2 * h);
-                        const uint64_t dP = desc_add(dP0, g * a.p_bytes), dV = desc_add(dV0, sv * a.v_tile_bytes);
-                        const uint32_t tO = tmem_O + g * 2 * a.dv_pad;
-                        mma_chain(tO, dP, dV, 2 * 2048, 2 * a.dv_pad * 16, LT_PAD / 16, idesc_v, 0);
-                        mma_chain(tO + a.dv_pad, desc_add(dP, (LT_PAD / 8) * 2048), desc_add(dV, (LT_PAD / 8) * (a.dv_pad * 16)), 2 * 2048,
-                                  2 * a.dv_pad * 16, LA_PAD / 16, idesc_v, 0);
-                        umma_commit(&bars[B_O_FULL + g]);
-                        umma_commit(&bars[B_V_EMPTY + sv]);
-                        if (++sv == a.nv) { sv = 0; pv ^= 1; }
-                        if (h < 8) S4_T(9 + 2 * h);
+                        if (hp < hs) {
+                            const int g = hp & 1;
+                            if (mbar_test_wait(&bars[B_P_FULL + g], (hp >> 1) & 1) && mbar_test_wait(&bars[B_V_FULL + sv], pv)) {
+                                tc_fence_after();
+                                if (hp < 8) S4_T(8 + 2 * hp);
+                                const uint64_t dP = desc_add(dP0, g * a.p_bytes), dV = desc_add(dV0, sv * a.v_tile_bytes);
+                                const uint32_t tO = tmem_O + g * 2 * a.dv_pad;
+                                mma_chain(tO, dP, dV, 2 * 2048, 2 * a.dv_pad * 16, LT_PAD / 16, idesc_v, 0);
+                                mma_chain(tO + a.dv_pad, desc_add(dP, (LT_PAD / 8) * 2048), desc_add(dV, (LT_PAD / 8) * (a.dv_pad * 16)), 2 * 2048,
+                                          2 * a.dv_pad * 16, LA_PAD / 16, idesc_v, 0);
+                                umma_commit(&bars[B_O_FULL + g]);
+                                umma_commit(&bars[B_V_EMPTY + sv]);
+                                if (++sv == a.nv) { sv = 0; pv ^= 1; }
+                                if (hp < 8) S4_T(9 + 2 * hp);
+                                ++hp;
+                                polls = 0;
+                            }
+                        }
                     }
                 }
                 umma_commit(&bars[B_PV_ALL]);
@@ -300,8 +299,8 @@ ipattn_site4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 tmem_ld16(tOa + c0, ra);
                 tmem_ld_wait();
                 asm volatile("" : "+r"(lt), "+r"(la) : : "memory");
-                const float w_t = a.Lt > 0 ? 1.0f / __uint_as_float(lt) : 0.f;
-                const float w_a = a.ap_scale / __uint_as_float(la);
+                const float w_t = a.Lt > 0 ? __fdividef(1.0f, __uint_as_float(lt)) : 0.f;
+                const float w_a = __fdividef(a.ap_scale, __uint_as_float(la));
                 reg_tie16(rt);
                 reg_tie16(ra);
                 float v[16];
@@ -311,9 +310,11 @@ ipattn_site4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
             if (a.d_pad <= 16 && !left) tmem_ld_wait();   // the two single-column loads above must still be retired
         };
-        // One-time skew: slot 1 starts when slot 0 enters its first exponential pass, so that from then on one slot's MUFU-bound
-        // pass runs under the other slot's tensor-memory / conversion / hand-off latency instead of both in lockstep.
-        if (slot == 1 && a.H > 2) named_bar_sync(7, 512);
+        // The exp2 passes of the two slots take turns (named barriers 8 / 9 are the token: "slot 0 / 1 may use the MUFU pipe"): a
+        // slot's two warpgroups put two warps on every sub-partition's MUFU pipe, which saturates it (one warp alone reaches ~70 %);
+        // the other slot's score loads, maxima, O conversion and barrier waits run underneath.  Every arrive has a taker.
+        const bool tok = a.H > 2;
+        if (tok && slot == 1) named_bar_arrive(8, 512);
 #pragma unroll 1
         for (int it = 0;; ++it) {
             const int h = slot + 2 * it;
@@ -361,7 +362,7 @@ ipattn_site4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             if (it > 0) convert_o(h - 2, (it - 1) & 1);
             if (!live) break;
             if (tr) S4_T(32 + it * 8 + 4);
-            if (it == 0 && slot == 0 && a.H > 2) named_bar_arrive(7, 512);
+            if (tok) named_bar_sync(8 + slot, 512);
             const float mxs_t = mx_t * sl, mxs_a = mx_a * sl;
             if (left) {
                 exp_store16<FMT>(s, sl, mxs_t, sP_row);
@@ -371,6 +372,7 @@ ipattn_site4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < NR16; ++c) exp_store16<FMT>(s + c * 16, sl, mxs_a, sP_row + (NL16 + c) * 2 * 2048);
             }
+            if (tok && h + 1 < a.H) named_bar_arrive(9 - slot, 512);   // the other slot's turn
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&bars[B_P_FULL + slot]);

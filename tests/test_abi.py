@@ -55,9 +55,10 @@ def test_no_compute_queries_work_without_gpu():
     assert lib.apx_ipattn_fused_ok(320, 8, 77, 8) == 1
     assert lib.apx_ipattn_fused_ok(256, 8, 8, 512) == 0 and lib.apx_ipattn_fused_ok(512, 16, 8, 32) == 0
     # kernel choice (measured policy, apx_api.cu::pick_site_kernel): all-heads wherever it applies, one-head for small grids at
-    # C = 320 / 384, three kernels at C = 640 and for large grids
+    # C <= 384 where it does not, three kernels at C = 640 and for large grids
     assert lib.apx_ipattn_site_kernel(2, 1000, 256, 8, 8, 128) == 1 and lib.apx_ipattn_site_kernel(16, 1000, 256, 8, 8, 128) == 1
     assert lib.apx_ipattn_site_kernel(2, 252, 384, 8, 8, 128) == 2 and lib.apx_ipattn_site_kernel(16, 252, 384, 8, 8, 128) == 0
+    assert lib.apx_ipattn_site_kernel(1, 100, 192, 4, 8, 128) == 2   # narrow site on a small grid: the one-head cluster kernel
     assert lib.apx_ipattn_site_kernel(2, 64, 640, 8, 8, 128) == 0
     assert lib.apx_set_site_variant(_lib.APX_SITE_ONEHEAD) == 0
     try:
