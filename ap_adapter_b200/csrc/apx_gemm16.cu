@@ -317,8 +317,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             mbar_wait(acc_bar, 0);
             tc_fence_after();
             if (te == 0) G16_TRACE(7);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
+            auto chunk = [&](int c, const uint4* rrc) {
                 const int tc = hf * (BN / 2) + c * 16;   // tile column of the chunk
                 uint32_t r[16];
                 tmem_ld16(taddr + tc, r);
@@ -330,12 +329,23 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const int oc = tc / (GEGLU ? 2 : 1);     // output column within the tile
 #pragma unroll
                 for (int k = 0; k < OPC / 8; ++k) {
-                    const uint4 o = pack8<FMT>(x + k * 8, has_res, rr[c][k]);
+                    const uint4 o = pack8<FMT>(x + k * 8, rrc != nullptr, rrc ? rrc[k] : make_uint4(0, 0, 0, 0));
                     const int occ = oc + k * 8;
                     const int box = occ >> 6, j = (occ & 63) >> 3;
                     const int js = ROW_BYTES == 128 ? (j ^ (trow & 7)) : j;   // 64-byte rows (GEGLU of a 64-column tile): plain layout
                     st_shared_v4(sbase + box * (BM * 128) + trow * ROW_BYTES + (js << 4), o.x, o.y, o.z, o.w);
                 }
+            };
+            if (has_res) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) chunk(c, rr[c]);   // unrolled: the prefetched residual words stay in registers
+            } else {
+                // This code runs ONCE per CTA, so part of what it costs is its instruction fetch (apx_ipattn_site.cu: -0.5 us per call for
+                // 800 fewer cold instructions): one chunk body instead of NCH copies of it (erf-GELU / GEGLU: ~350 instructions each).
+                // Back-to-back replays of one GEMM keep the code warm and read the same either way (profiles/r3e_gemm16_epilogue_ab.txt:
+                // 3.84 vs 3.87 ms over the step's GEMM mix).
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) chunk(c, nullptr);
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
             named_bar_sync(1, NEPI);
