@@ -341,7 +341,7 @@ ipattn_site_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 int hs = 0, hp = 0;
                 uint32_t polls = 0;
                 while (hp < a.hg) {
-                    if (++polls > (1u << 26)) asm volatile("trap;");   // a protocol bug becomes a CUDA error, not a hung GPU
+                    if (++polls > (1u << 30)) asm volatile("trap;");   // a protocol bug becomes a CUDA error (after ~30 s), not a hung GPU
                     if (hs < a.hg) {
                         const int g = hs & 1;
                         if (mbar_test_wait(&bars[B_K_FULL + sk], pk) && (hs < 2 || mbar_test_wait(&bars[B_S_FREE + g], ((hs >> 1) - 1) & 1))) {

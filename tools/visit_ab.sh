@@ -1,5 +1,7 @@
 #!/bin/bash
-# GPU visit: A/B runs of harness cases under environment switches.  usage: tools/visit_ab.sh TAG < lines of "ENV=.. ENV=.. | case-filter | trace?"
+# GPU visit: A/B runs of harness cases under environment switches / library variants (the A/B logs under profiles/r2p..r3a were made
+# with it).  usage: tools/visit_ab.sh TAG < lines of "ENV=.. LD_LIBRARY_PATH=variants/NAME | case-filter | trace?"
+# (variants/NAME/libapx.so: tools/build_variant.sh NAME file.cu "-DMACRO=1")
 set -u
 mkdir -p gpurun_out
 TAG=${1:-ab}
