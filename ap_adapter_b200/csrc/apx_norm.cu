@@ -9,6 +9,7 @@
 #include "apx_internal.h"
 #include "apx_ptx.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace apx {
 namespace {
@@ -131,6 +132,111 @@ __global__ void __launch_bounds__(512) groupnorm_nhwc_kernel(GnArgs a, int cs) {
     }
 }
 
+// Second form (round 2, second half): the same decomposition, with the latency chain of a small tensor cut down — most of the 109
+// calls of a denoise step normalise 40 KB ... 1 MB and ran 7 - 8 us, of which the dependent global round trips were the bulk:
+//   * the per-channel constants of the group (conv bias + time-embedding row, gamma, beta: cpg <= 64 values each) are loaded ONCE into
+//     shared memory while the first batch of x loads is in flight, instead of three extra global loads per 4-channel item;
+//   * no dependent "first value" load for the shift: the statistics are two passes over the values already staged in shared memory
+//     (local mean, then local sum of squared deviations), merged across the cluster with Chan's update — one exchange, and better
+//     conditioned than the shifted single pass.
+__global__ void __launch_bounds__(512) groupnorm_nhwc_v2_kernel(GnArgs a, int cs) {
+    extern __shared__ float sv[];           // [HW_r][cpg]
+    __shared__ float red[32];
+    __shared__ float4 part[8];              // (mean, M2, count) of every CTA of the cluster, written by their owners
+    __shared__ float s_add[64], s_ga[64], s_be[64];
+    const int g = blockIdx.x / cs, r = blockIdx.x - g * cs, b = blockIdx.y;
+    const int q4 = a.cpg / 4;               // 4-channel (8-byte) pieces per pixel of this group
+    const int p_lo = static_cast<int>(static_cast<uint32_t>(a.HW) * r / cs), p_hi = static_cast<int>(static_cast<uint32_t>(a.HW) * (r + 1) / cs);   // HW * 8 fits 32 bits
+    const int n4 = (p_hi - p_lo) * q4;
+    const uint16_t* xg = a.x + (static_cast<size_t>(b) * a.HW + p_lo) * a.C + g * a.cpg;
+    uint16_t* yg = a.y + (static_cast<size_t>(b) * a.HW + p_lo) * a.C + g * a.cpg;
+    const int step = blockDim.x;
+    // first batch of x loads (up to four 8-byte pieces per thread) goes out before anything else
+    uint2 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * step;
+        raw[u] = make_uint2(0, 0);
+        if (i < n4) { const int p = i / q4, q = i - p * q4; raw[u] = *reinterpret_cast<const uint2*>(xg + static_cast<size_t>(p) * a.C + q * 4); }
+    }
+    if (threadIdx.x < a.cpg) {
+        const int c = g * a.cpg + threadIdx.x;
+        float add = a.chan_bias ? a.chan_bias[c] : 0.f;
+        if (a.bc_add) add += ld16f(a.bc_add, static_cast<size_t>(b) * a.bc_stride + c, a.fmt);
+        s_add[threadIdx.x] = add;
+        s_ga[threadIdx.x] = a.gamma[c];
+        s_be[threadIdx.x] = a.beta[c];
+    }
+    __syncthreads();
+    float s1 = 0.f;
+    auto stage = [&](int i, uint2 w) {
+        const int q = i % q4;
+        float v0, v1, v2, v3;
+        unpack16(w.x, a.fmt, v0, v1);
+        unpack16(w.y, a.fmt, v2, v3);
+        const float4 ad = *reinterpret_cast<const float4*>(s_add + q * 4);
+        v0 += ad.x; v1 += ad.y; v2 += ad.z; v3 += ad.w;
+        *reinterpret_cast<float4*>(sv + i * 4) = make_float4(v0, v1, v2, v3);
+        s1 += (v0 + v1) + (v2 + v3);
+    };
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (threadIdx.x + u * step < n4) stage(threadIdx.x + u * step, raw[u]);
+    for (int i0 = threadIdx.x + 4 * step; i0 < n4; i0 += 4 * step) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * step;
+            if (i < n4) { const int p = i / q4, q = i - p * q4; raw[u] = *reinterpret_cast<const uint2*>(xg + static_cast<size_t>(p) * a.C + q * 4); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * step < n4) stage(i0 + u * step, raw[u]);
+    }
+    // local statistics: mean of this CTA's values, then the sum of squared deviations from it (every thread re-reads its own items)
+    const float n_loc = static_cast<float>(n4) * 4.f;
+    const float mean_loc = block_sum(s1, red) / fmaxf(n_loc, 1.f);
+    float m2 = 0.f;
+    for (int i = threadIdx.x; i < n4; i += step) {
+        const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
+        const float d0 = v.x - mean_loc, d1 = v.y - mean_loc, d2 = v.z - mean_loc, d3 = v.w - mean_loc;
+        m2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, m2))));
+    }
+    m2 = block_sum(m2, red);
+    float mean = mean_loc;
+    if (cs > 1) {
+        if (threadIdx.x < cs) {             // thread t publishes this CTA's (mean, M2, count) in CTA t's table
+            const uint32_t dst = map_to_cta(smem_u32(&part[r]), threadIdx.x);
+            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(mean_loc), "f"(m2), "f"(n_loc), "f"(0.f) : "memory");
+        }
+        cluster_sync_all();
+        // Chan's merge over the CTAs of the cluster
+        float tot = 0.f, msum = 0.f;
+        for (int i = 0; i < cs; ++i) { tot += part[i].z; msum += part[i].z * part[i].x; }
+        mean = msum / tot;
+        m2 = 0.f;
+        for (int i = 0; i < cs; ++i) {
+            const float d = part[i].x - mean;
+            m2 += part[i].y + part[i].z * d * d;
+        }
+    }
+    const float rstd = rsqrtf(m2 / (static_cast<float>(a.HW) * a.cpg) + a.eps);
+    for (int i = threadIdx.x; i < n4; i += step) {
+        const int p = i / q4, q = i - p * q4;
+        const float4 v = *reinterpret_cast<const float4*>(sv + i * 4);
+        const float4 ga = *reinterpret_cast<const float4*>(s_ga + q * 4), be = *reinterpret_cast<const float4*>(s_be + q * 4);
+        float o[4] = {(v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y, (v.z - mean) * rstd * ga.z + be.z,
+                      (v.w - mean) * rstd * ga.w + be.w};
+        if (a.silu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + __expf(-o[k]));
+        }
+        uint2 out;
+        out.x = pack16(o[0], o[1], a.fmt);
+        out.y = pack16(o[2], o[3], a.fmt);
+        *reinterpret_cast<uint2*>(yg + static_cast<size_t>(p) * a.C + q * 4) = out;
+    }
+}
+
 // y = (a + b + bias[c]) * scale over [rows, C] 16-bit, 8 channels (16 bytes) per thread
 __global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const uint4* __restrict__ A, const uint4* __restrict__ Bm, const float* __restrict__ bias,
                                                            uint4* __restrict__ Y, size_t n8, int C8, float scale, int fmt) {
@@ -179,7 +285,10 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
                 APX_EINVAL, "apx_groupnorm_nhwc: misaligned pointer / bad bc_add stride");
     static std::atomic<uint64_t> attr_mask{0};
     if (first_use_on_device(attr_mask))
+    {
         APX_CUDA(cudaFuncSetAttribute(groupnorm_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        APX_CUDA(cudaFuncSetAttribute(groupnorm_nhwc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     GnArgs a{static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), gamma, beta, chan_bias, static_cast<const uint16_t*>(bc_add), bc_stride,
              B, HW, C, groups, cpg, eps, silu ? 1 : 0, dtype == APX_F16 ? 0 : 1};
     // a group is split over a cluster of 1 / 2 / 4 / 8 CTAs so that a CTA owns ~<= 2048 four-channel items (8 per thread at 256 threads):
@@ -188,7 +297,10 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
     int cs = 1;
     while (cs < 8 && (n4 / cs > 2048 || static_cast<size_t>(HW) * cpg * 4 / cs > 200 * 1024) && HW / (2 * cs) >= 1) cs *= 2;
     const int per = (n4 + cs - 1) / cs;
-    const int threads = per >= 1024 ? 256 : per >= 256 ? 128 : 64;
+    static const bool v1 = [] { const char* e = getenv("APX_GN_V1"); return e && e[0] == '1'; }();
+    const bool use_v1 = v1 || cpg > 64;
+    // second form: at most four 8-byte items per thread, so that every x load of a CTA is in flight at once
+    const int threads = use_v1 ? (per >= 1024 ? 256 : per >= 256 ? 128 : 64) : (per > 1024 ? 512 : per > 512 ? 256 : per > 256 ? 128 : 64);
     const size_t smem = (static_cast<size_t>((HW + cs - 1) / cs) + 1) * cpg * 4;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(groups * cs), B);
@@ -202,7 +314,8 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = cs > 1 ? 1 : 0;
-    APX_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_nhwc_kernel, a, cs));
+    if (use_v1) APX_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_nhwc_kernel, a, cs));
+    else APX_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_nhwc_v2_kernel, a, cs));
     APX_LAUNCH_CHECK("groupnorm_nhwc_kernel");
     return APX_OK;
 }
