@@ -98,3 +98,21 @@ def test_oracle_against_live_reference_processor():
         y = ipattn_oracle.ipattn_forward(x, ctx, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, proc.to_k_ip.weight,
                                          proc.to_v_ip.weight, attn.to_out[0].weight, attn.to_out[0].bias, h, lt, 0.7)
     assert ((y - y_ref).abs().max() / y_ref.abs().max()).item() < TOL
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(ref_shims.REF_BUILT, "MANIFEST.json")), reason="oracle/_ref not built (oracle/build_ref.py)")
+def test_oracle_ref_is_the_unmodified_reference_module():
+    """oracle/_ref holds the reference's processor module byte for byte: the recorded sha256 matches the file and, where the
+    reference tree is mounted, the file it was taken from."""
+    import hashlib
+    import json
+
+    with open(os.path.join(ref_shims.REF_BUILT, "MANIFEST.json")) as f:
+        manifest = json.load(f)
+    for name, rec in manifest["files"].items():
+        with open(os.path.join(ref_shims.REF_BUILT, name), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == rec["sha256"], name
+        src = os.path.join(ref_shims.REF_ROOT, rec["from"])
+        if os.path.isfile(src):
+            with open(src, "rb") as f:
+                assert hashlib.sha256(f.read()).hexdigest() == rec["sha256"], src
