@@ -65,6 +65,7 @@ SYMBOLS = {
     "apx_resample": (_I, [_P, _I, _I, _P, _I, _I, _I, _P, _P]),
     "apx_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _L, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "apx_add_bias_nhwc": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
+    "apx_add_layernorm": (_I, [_P, _P, _P, _P, _I, _P, _P, _L, _I, _F, _I, _P]),
     "apx_audiomae_workspace_bytes": (_Z, [_I]),
     "apx_audiomae_fwd": (_I, [_P, POINTER(VitWeights), _P, _I, _I, _I, _P, _Z, _P]),
     "apx_audiomae_encode": (_I, [_P, POINTER(VitWeights), _P, _I, _P, _Z, _P]),
@@ -323,6 +324,29 @@ def add_bias_nhwc(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None, s
         check(lib.apx_add_bias_nhwc(ptr(a), ptr(b), ptr(bias), ptr(y), n * h * w, c, float(scale), dtype_code(a.dtype), stream_ptr()),
               "apx_add_bias_nhwc")
     return y
+
+
+def add_layernorm_ok(x: torch.Tensor, norm) -> bool:
+    """Shapes / modules apx_add_layernorm takes: a contiguous 16-bit (..., C) tensor, C % 8 == 0, C <= 2048, an affine LayerNorm over C."""
+    w = getattr(norm, "weight", None)
+    return (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and x.is_contiguous() and x.shape[-1] % 8 == 0 and x.shape[-1] <= 2048
+            and w is not None and norm.bias is not None and tuple(norm.normalized_shape) == (x.shape[-1],)
+            and w.dtype in (x.dtype, torch.float32) and norm.bias.dtype == w.dtype and w.is_contiguous() and norm.bias.is_contiguous())
+
+
+def add_layernorm(a: torch.Tensor, b: torch.Tensor | None, norm) -> tuple[torch.Tensor | None, torch.Tensor]:
+    """(a + b, LayerNorm(a + b)) in one kernel (apx_add_layernorm); b None: (None, LayerNorm(a)).  `norm` is the nn.LayerNorm."""
+    lib = load()
+    w, bias = norm.weight.detach(), norm.bias.detach()
+    dev = require_cuda(a, b, w, bias)
+    assert b is None or (b.shape == a.shape and b.dtype == a.dtype and b.is_contiguous())
+    c = a.shape[-1]
+    y_ln = torch.empty_like(a)
+    y_sum = torch.empty_like(a) if b is not None else None
+    with torch.cuda.device(dev):
+        check(lib.apx_add_layernorm(ptr(a), ptr(b), ptr(w), ptr(bias), dtype_code(w.dtype), ptr(y_sum), ptr(y_ln), a.numel() // c, c,
+                                    float(norm.eps), dtype_code(a.dtype), stream_ptr()), "apx_add_layernorm")
+    return y_sum, y_ln
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:

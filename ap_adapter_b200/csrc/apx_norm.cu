@@ -261,6 +261,95 @@ __global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const uint4* __restr
     }
 }
 
+// h = a + b (16-bit, stored when b is given) and x = LayerNorm(h) * gamma + beta in ONE pass: the residual add of a transformer block and
+// the LayerNorm of the next sub-block (diffusers' BasicTransformerBlock: "hidden_states = attn_output + hidden_states;
+// norm_hidden_states = self.norm2(hidden_states)"), which the stock graph runs as two ATen kernels of 1.8 + 3.5 us at the UNet's small
+// sites (128 x 640, 504 x 384).  One warp per row, every load of the row (a, b, gamma, beta) in flight before the first use, statistics in
+// fp32 over the ROUNDED sum (what LayerNorm would read back), two exact passes in registers.  NP = 16-byte pieces per lane.
+template <int NP>
+__global__ void __launch_bounds__(256) add_layernorm16_kernel(const uint4* __restrict__ A, const uint4* __restrict__ Bm, const void* __restrict__ gamma,
+                                                             const void* __restrict__ beta, int w_f32, uint4* __restrict__ Ysum,
+                                                             uint4* __restrict__ Yln, int rows, int C8, float eps, int fmt) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t base = static_cast<size_t>(row) * C8;
+    uint4 a[NP], b[NP];
+    float g[NP][8], be[NP][8];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int c8 = i * 32 + lane;
+        a[i] = make_uint4(0, 0, 0, 0); b[i] = make_uint4(0, 0, 0, 0);
+        if (c8 < C8) {
+            a[i] = A[base + c8];
+            if (Bm) b[i] = Bm[base + c8];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int c8 = i * 32 + lane;
+        if (c8 < C8) {
+            if (w_f32) {
+                const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c8], g1 = reinterpret_cast<const float4*>(gamma)[2 * c8 + 1];
+                const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * c8], b1 = reinterpret_cast<const float4*>(beta)[2 * c8 + 1];
+                g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+                be[i][0] = b0.x; be[i][1] = b0.y; be[i][2] = b0.z; be[i][3] = b0.w; be[i][4] = b1.x; be[i][5] = b1.y; be[i][6] = b1.z; be[i][7] = b1.w;
+            } else {
+                const uint4 gw = reinterpret_cast<const uint4*>(gamma)[c8], bw = reinterpret_cast<const uint4*>(beta)[c8];
+                unpack16(gw.x, fmt, g[i][0], g[i][1]); unpack16(gw.y, fmt, g[i][2], g[i][3]);
+                unpack16(gw.z, fmt, g[i][4], g[i][5]); unpack16(gw.w, fmt, g[i][6], g[i][7]);
+                unpack16(bw.x, fmt, be[i][0], be[i][1]); unpack16(bw.y, fmt, be[i][2], be[i][3]);
+                unpack16(bw.z, fmt, be[i][4], be[i][5]); unpack16(bw.w, fmt, be[i][6], be[i][7]);
+            }
+        }
+    }
+    float v[NP][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int c8 = i * 32 + lane;
+        const uint32_t aw[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, bw[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+        uint32_t hw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a0, a1, b0, b1;
+            unpack16(aw[k], fmt, a0, a1);
+            unpack16(bw[k], fmt, b0, b1);
+            hw[k] = pack16(a0 + b0, a1 + b1, fmt);              // the 16-bit residual stream, rounded once
+            unpack16(hw[k], fmt, v[i][2 * k], v[i][2 * k + 1]);  // LayerNorm reads the rounded value back
+        }
+        if (c8 < C8) {
+            if (Bm) Ysum[base + c8] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[i][k];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float n = static_cast<float>(C8) * 8.f, mean = s / n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (i * 32 + lane < C8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; q = fmaf(d, d, q); }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / n + eps);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int c8 = i * 32 + lane;
+        if (c8 < C8) {
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                ow[k] = pack16((v[i][2 * k] - mean) * rstd * g[i][2 * k] + be[i][2 * k],
+                               (v[i][2 * k + 1] - mean) * rstd * g[i][2 * k + 1] + be[i][2 * k + 1], fmt);
+            Yln[base + c8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace apx
 
@@ -332,6 +421,35 @@ int apx_add_bias_nhwc(const void* a, const void* b, const float* bias, void* y, 
     add_bias_nhwc_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b), bias,
                                                                                static_cast<uint4*>(y), n8, C / 8, scale, dtype == APX_F16 ? 0 : 1);
     APX_LAUNCH_CHECK("add_bias_nhwc_kernel");
+    return APX_OK;
+}
+
+int apx_add_layernorm(const void* a, const void* b, const void* gamma, const void* beta, int w_dtype, void* y_sum, void* y_ln, int64_t rows, int C,
+                      float eps, int dtype, void* stream) {
+    APX_REQUIRE(a && gamma && beta && y_ln && ((b == nullptr) == (y_sum == nullptr)), APX_EINVAL,
+                "apx_add_layernorm: null pointer (b and y_sum come together)");
+    APX_REQUIRE(rows > 0 && rows <= (1ll << 30) && C > 0 && C % 8 == 0 && C <= 2048, APX_EUNSUPPORTED,
+                "apx_add_layernorm: rows=%lld C=%d (C %% 8 == 0, C <= 2048)", static_cast<long long>(rows), C);
+    APX_REQUIRE(dtype == APX_F16 || dtype == APX_BF16, APX_EUNSUPPORTED, "apx_add_layernorm: dtype %d", dtype);
+    APX_REQUIRE(w_dtype == dtype || w_dtype == APX_F32, APX_EUNSUPPORTED, "apx_add_layernorm: gamma / beta dtype %d (the activations' or fp32)", w_dtype);
+    APX_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                  reinterpret_cast<uintptr_t>(y_sum) | reinterpret_cast<uintptr_t>(y_ln)) & 15) == 0,
+                APX_EINVAL, "apx_add_layernorm: pointers must be 16-byte aligned");
+    const int C8 = C / 8, np = (C8 + 31) / 32;
+    const int fmt = dtype == APX_F16 ? 0 : 1, wf = w_dtype == APX_F32 ? 1 : 0;
+    const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint4 *A = static_cast<const uint4*>(a), *Bm = static_cast<const uint4*>(b);
+    uint4 *Ys = static_cast<uint4*>(y_sum), *Yl = static_cast<uint4*>(y_ln);
+    const int r = static_cast<int>(rows);
+    switch (np) {
+        case 1: add_layernorm16_kernel<1><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 2: add_layernorm16_kernel<2><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 3: add_layernorm16_kernel<3><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 4: add_layernorm16_kernel<4><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        default: add_layernorm16_kernel<8><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+    }
+    APX_LAUNCH_CHECK("add_layernorm16_kernel");
     return APX_OK;
 }
 

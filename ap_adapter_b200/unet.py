@@ -237,6 +237,9 @@ class BasicTransformerBlock(nn.Module):
     # class-wide switch (APX_FOLD_RESIDUAL): "ip" (default) only the adapter sites, which add in place; "1" also the plain sites
     # (to_out + residual through libapx's GEMM — measured 0.37 ms per step SLOWER than cuBLAS + add on B200, kept opt-in); "0" none
     fold_residual = {"0": False, "1": True}.get(os.environ.get("APX_FOLD_RESIDUAL", "ip"), "ip")
+    # inference on CUDA: where norm1 / norm2 are not folded into the next projection (the sites below 1000 rows), attn1's residual add and
+    # norm2 run as ONE libapx kernel (apx_add_layernorm) and norm1 as its LayerNorm-only form; APX_ADD_LN=0 keeps the ATen kernels
+    add_ln = os.environ.get("APX_ADD_LN", "1") != "0"
 
     def __init__(self, dim: int, heads: int, dim_head: int, cross_attention_dim: Optional[int],
                  double_self_attention: bool = False, only_cross_attention: bool = False):
@@ -262,21 +265,35 @@ class BasicTransformerBlock(nn.Module):
         ehs1 = encoder_hidden_states if self.only_cross_attention else None
         p1 = self.attn1.processor
         kw1 = dict(kw)
+        infer = h.is_cuda and not torch.is_grad_enabled() and not h.requires_grad
         if hasattr(p1, "can_fold_norm") and p1.can_fold_norm(self.attn1, h, self.norm1):
             x, kw1["fold_norm"] = h, self.norm1          # norm1 runs inside the site's QKV projection
+        elif self.add_ln and infer and h.is_contiguous() and _lib.add_layernorm_ok(h, self.norm1):
+            x = _lib.add_layernorm(h, None, self.norm1)[1]   # libapx LayerNorm (one warp per row, every load in flight at once)
         else:
             x = self.norm1(h)
+        a1 = None
         if fold is True and getattr(p1, "accepts_residual", False):
             h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, residual_inout=h, **kw1)
         else:
-            h = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, **kw1) + h
-        if self.attn2 is not None:
+            a1 = self.attn1(x, encoder_hidden_states=ehs1, attention_mask=attention_mask, **kw1)   # residual add below
+        if self.attn2 is None:
+            if a1 is not None:
+                h = a1 + h
+        else:
             # the adapter hot path: attn2's input is norm2(h), its output is residual-added right here
             p2 = self.attn2.processor
             kw2 = dict(kw)
-            if hasattr(p2, "can_fold_norm") and p2.can_fold_norm(self.attn2, h, self.norm2, encoder_hidden_states):
+            fold2 = hasattr(p2, "can_fold_norm") and p2.can_fold_norm(self.attn2, h, self.norm2, encoder_hidden_states)
+            x = None
+            if a1 is not None:
+                if (not fold2 and self.add_ln and infer and a1.shape == h.shape and h.is_contiguous() and _lib.add_layernorm_ok(a1, self.norm2)):
+                    h, x = _lib.add_layernorm(a1, h, self.norm2)   # attn1's residual add + norm2 in one kernel (apx_add_layernorm)
+                else:
+                    h = a1 + h
+            if fold2:
                 x, kw2["fold_norm"] = h, self.norm2      # norm2 folded into the adapter site kernel / a plain site's Q(KV) projection
-            else:
+            elif x is None:
                 x = self.norm2(h)
             if fold and getattr(p2, "accepts_residual", False) and (fold is True or getattr(p2, "folds_in_place", False)):
                 h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask,

@@ -82,7 +82,7 @@ HOST_GRAPH = ("adapter sites: libapx (all-heads site kernel at C=256, one-head c
               "token view, one GEMM for all time-embedding projections; LayerNorms folded into the libapx GEMMs (norm3 -> GEGLU projection "
               "everywhere, norm1 / norm2 -> Q(KV) projection at sites with >= 1000 rows, norm2 -> site kernel at C=256); plain attention "
               "sites: fused QKV projection (cuBLAS below 1000 rows), self-attention core in libapx (apx_flash_attention) while its grid fits "
-              "one wave, cuDNN SDPA otherwise and at the masked T5 sites, to_out on cuBLAS; T5 K/V projected once per context; one CUDA "
+              "one wave, cuDNN SDPA otherwise and at the masked T5 sites, to_out on cuBLAS; at the sites below 1000 rows attn1's residual add + norm2 in one libapx kernel and norm1 as its LayerNorm-only form; T5 K/V projected once per context; one CUDA "
               "graph per step")
 
 
@@ -758,12 +758,13 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
     from ap_adapter_b200.pipeline import APAdapterDenoiser
     from ap_adapter_b200.unet import NHWC, BasicTransformerBlock, FeedForward, build_attn_processors
     saved = (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled, AttnProcessor2_0.cache_context,
-             AttnProcessor2_0.flash_min_keys)
+             AttnProcessor2_0.flash_min_keys, BasicTransformerBlock.add_ln)
     dev = lat0.device
     try:
         FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
         AttnProcessor2_0.cache_context = False
         AttnProcessor2_0.flash_min_keys = 1 << 30     # the stock graph keeps torch's SDPA everywhere
+        BasicTransformerBlock.add_ln = False          # ... and ATen's residual adds / LayerNorms
         theirs = build_attn_processors(unet, _TorchIPAttnSite, ap_scale=AP_SCALE, device=dev, dtype=torch.float16)
         for k, p in ours.items():
             if hasattr(p, "to_k_ip"):
@@ -796,7 +797,7 @@ def torch_gpu_step(unet, ours, lat0, gpe, pe, mask, ts, coefs, steps: int) -> di
                         "unfused FeedForward / projections / residual adds, one CUDA graph per step, device-timed"}
     finally:
         (FeedForward.use_fused, AttnProcessor2_0.fuse_projections, BasicTransformerBlock.fold_residual, NHWC.enabled,
-         AttnProcessor2_0.cache_context, AttnProcessor2_0.flash_min_keys) = saved
+         AttnProcessor2_0.cache_context, AttnProcessor2_0.flash_min_keys, BasicTransformerBlock.add_ln) = saved
         unet.set_attn_processor(dict(ours))
 
 

@@ -231,6 +231,13 @@ int apx_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, con
 /* y = (a + b + bias[c]) * scale over [rows, C] `dtype` (C % 8 == 0); bias fp32[C] or NULL.  ResnetBlock2D's output:
  * (shortcut(x) + conv2(h) + conv biases) / output_scale_factor. */
 int apx_add_bias_nhwc(const void* a, const void* b, const float* bias, void* y, int64_t rows, int C, float scale, int dtype, void* stream);
+/* y_sum = a + b (rounded to `dtype`, the new residual stream) and y_ln = LayerNorm(y_sum) * gamma + beta, in one kernel; b == NULL (then
+ * y_sum == NULL): y_ln = LayerNorm(a).  a, b, y_sum, y_ln [rows, C] `dtype` (C % 8 == 0, C <= 2048); gamma, beta [C] in `w_dtype` (= dtype or
+ * APX_F32).  Statistics in fp32 over the rounded sum, two exact passes.  Replaces "hidden_states = attn_output + hidden_states;
+ * norm_hidden_states = self.norm2(hidden_states)" of diffusers' BasicTransformerBlock as wired around every attn2 call site by
+ * pipeline/modeling_audioldm2.py:1140-1156, 1317-1333, 1492-1508 (third-party leaf). */
+int apx_add_layernorm(const void* a, const void* b, const void* gamma, const void* beta, int w_dtype, void* y_sum, void* y_ln, int64_t rows,
+                      int C, float eps, int dtype, void* stream);
 
 /* ---- AudioMAE encoder ---------------------------------------------------------------- */
 typedef struct apx_vit_block {

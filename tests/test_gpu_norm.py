@@ -96,9 +96,50 @@ def test_unet_channels_last_route_matches_stock_graph():
             n_nhwc = _lib.launch_count() - n0
     finally:
         NHWC.enabled = saved
-    # 44 resnet GroupNorms + 64 transformer GroupNorms + conv_norm_out, 22 resnet output adds
-    assert n_nhwc - n_stock == 109 + 22, (n_nhwc, n_stock)
+    # 44 resnet GroupNorms + 64 transformer GroupNorms + conv_norm_out, 22 resnet output adds; and, in the 44 Transformer2DModels below
+    # 1000 rows, the two apx_add_layernorm calls of the block: the stock route hands it a STRIDED token view of the NCHW tensor
+    # (strides (C*HW, 1, HW)), which that kernel does not take — ATen's LayerNorm and add run there — the channels-last view is contiguous
+    from ap_adapter_b200.unet import BasicTransformerBlock
+    assert n_nhwc - n_stock == 109 + 22 + (88 if BasicTransformerBlock.add_ln else 0), (n_nhwc, n_stock)
     assert y.shape == y_stock.shape and y.is_contiguous() and torch.isfinite(y).all()
     err = rel_err(y, y_stock)
     record("unet/channels_last_vs_stock", err=err)
     assert err < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("wdtype", ["same", "f32"])
+@pytest.mark.parametrize("shape", [(2, 64, 640), (2, 252, 384), (2, 1000, 256), (1, 7, 320), (3, 5, 2048), (2, 33, 1280)])
+def test_add_layernorm_matches_torch(shape, wdtype, dtype):
+    """apx_add_layernorm: y_sum is the 16-bit sum torch forms (one rounding: bitwise equal), y_ln the LayerNorm of that rounded sum
+    (fp32 reference on the same 16-bit inputs; bar 2x the measured error); the LayerNorm-only form (b = None) likewise."""
+    torch.manual_seed(sum(shape))
+    c = shape[-1]
+    a = (torch.randn(shape) * 0.7).to(dtype).cuda()
+    b = (torch.randn(shape) * 1.3 + 0.2).to(dtype).cuda()
+    norm = torch.nn.LayerNorm(c, eps=1e-5).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(c) + 0.5)
+        norm.bias.copy_(torch.randn(c) * 0.1)
+    norm = norm.to(dtype) if wdtype == "same" else norm
+    assert _lib.add_layernorm_ok(a, norm)
+    n0 = _lib.launch_count()
+    y_sum, y_ln = _lib.add_layernorm(a, b, norm)
+    _, y_only = _lib.add_layernorm(a, None, norm)
+    assert _lib.launch_count() == n0 + 2
+    h = a + b
+    assert torch.equal(y_sum, h)
+    w32, b32 = norm.weight.float(), norm.bias.float()
+    ref = torch.nn.functional.layer_norm(h.float(), (c,), w32, b32, 1e-5)
+    ref_only = torch.nn.functional.layer_norm(a.float(), (c,), w32, b32, 1e-5)
+    err, err_only = rel_err(y_ln, ref), rel_err(y_only, ref_only)
+    record("add_layernorm/" + "x".join(map(str, shape)), dtype=str(dtype), wdtype=wdtype, err=err, err_ln_only=err_only)
+    tol = 8e-4 if dtype == torch.float16 else 6e-3   # the output rounding: 2^-11 / 2^-8 of the largest value, x 1.5
+    assert err < tol and err_only < tol, (err, err_only)
+
+
+def test_add_layernorm_rejects_what_it_does_not_cover():
+    norm = torch.nn.LayerNorm(100).cuda().half()
+    assert not _lib.add_layernorm_ok(torch.zeros(4, 100, device="cuda", dtype=torch.float16), norm)          # C % 8
+    assert not _lib.add_layernorm_ok(torch.zeros(4, 104, device="cuda", dtype=torch.float32), torch.nn.LayerNorm(104).cuda())   # fp32 activations
+    assert not _lib.add_layernorm_ok(torch.zeros(4, 104, device="cuda", dtype=torch.float16), torch.nn.LayerNorm(104, elementwise_affine=False).cuda())

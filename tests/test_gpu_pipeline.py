@@ -65,6 +65,7 @@ def test_config3_end_to_end_matches_the_oracle_chain(world):
     assert ctx_err < 1.5e-3                                      # AudioMAE with fp16 GEMM operands + fp16 context storage (measured 5.5e-4)
     unet.set_attn_processor(dict(theirs))
     FeedForward.use_fused = AttnProcessor2_0.fuse_projections = BasicTransformerBlock.fold_residual = NHWC.enabled = False
+    add_ln, BasicTransformerBlock.add_ln = BasicTransformerBlock.add_ln, False
     try:
         ref_den = APAdapterDenoiser(unet)
         want = ref_den.denoise(cu(inp["lat"]).half(), cu(ctx).half(), cu(inp["pe"]).half(), cu(inp["mask"]),
@@ -72,6 +73,7 @@ def test_config3_end_to_end_matches_the_oracle_chain(world):
     finally:
         FeedForward.use_fused = AttnProcessor2_0.fuse_projections = NHWC.enabled = True
         BasicTransformerBlock.fold_residual = "ip"
+        BasicTransformerBlock.add_ln = add_ln
         unet.set_attn_processor(dict(ours))
     err = rel_err(got, want)
     record("config3/latents_after_3_steps", err=err)
