@@ -64,15 +64,19 @@ def test_block_takes_fused_route_and_matches_unfused():
     h = torch.randn(2, 400, 256, device="cuda", dtype=torch.float16)      # 800 rows: below the Q(KV) LayerNorm-fold threshold
     with torch.no_grad():
         BasicTransformerBlock.fold_residual = True
+        add_ln = BasicTransformerBlock.add_ln
         try:
             n0 = _lib.launch_count()
             y = blk(h)
-            # attn1's self-attention core (400 keys, d = 64) and its to_out + residual GEMM (opt-in), the two FeedForward GEMMs
-            assert _lib.launch_count() - n0 == 4
+            # norm1 as libapx's LayerNorm (apx_add_layernorm without an addend), attn1's self-attention core (400 keys, d = 64) and its
+            # to_out + residual GEMM (opt-in), the two FeedForward GEMMs
+            assert _lib.launch_count() - n0 == 4 + (1 if BasicTransformerBlock.add_ln else 0)
             FeedForward.use_fused = BasicTransformerBlock.fold_residual = False
+            BasicTransformerBlock.add_ln = False
             y_ref = blk(h)
         finally:
             FeedForward.use_fused, BasicTransformerBlock.fold_residual = True, "ip"
+            BasicTransformerBlock.add_ln = add_ln
     assert rel_err(y, y_ref) < 2e-3
     # grad mode keeps the differentiable torch graph
     n0 = _lib.launch_count()
