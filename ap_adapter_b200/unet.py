@@ -235,7 +235,8 @@ class BasicTransformerBlock(nn.Module):
     """norm1 -> attn1 -> +res; norm2 -> attn2(ctx) -> +res; norm3 -> GEGLU FF -> +res."""
 
     # class-wide switch (APX_FOLD_RESIDUAL): "ip" (default) only the adapter sites, which add in place; "1" also the plain sites
-    # (to_out + residual through libapx's GEMM — measured 0.37 ms per step SLOWER than cuBLAS + add on B200, kept opt-in); "0" none
+    # (to_out + residual through libapx's GEMM — measured 0.37 ms per step slower than cuBLAS + add on B200 with the round-1 GEMM, 0.09 ms
+    # slower with gemm16 and apx_add_layernorm (8.39 vs 8.30 ms, profiles/r3o_bench_b1_fold_residual_all.json): kept opt-in); "0" none
     fold_residual = {"0": False, "1": True}.get(os.environ.get("APX_FOLD_RESIDUAL", "ip"), "ip")
     # inference on CUDA: where norm1 / norm2 are not folded into the next projection (the sites below 1000 rows), attn1's residual add and
     # norm2 run as ONE libapx kernel (apx_add_layernorm) and norm1 as its LayerNorm-only form; APX_ADD_LN=0 keeps the ATen kernels
@@ -294,7 +295,10 @@ class BasicTransformerBlock(nn.Module):
             if fold2:
                 x, kw2["fold_norm"] = h, self.norm2      # norm2 folded into the adapter site kernel / a plain site's Q(KV) projection
             elif x is None:
-                x = self.norm2(h)
+                if self.add_ln and infer and h.is_contiguous() and _lib.add_layernorm_ok(h, self.norm2):
+                    x = _lib.add_layernorm(h, None, self.norm2)[1]   # (attn1 folded its own residual add: LayerNorm-only form)
+                else:
+                    x = self.norm2(h)
             if fold and getattr(p2, "accepts_residual", False) and (fold is True or getattr(p2, "folds_in_place", False)):
                 h = self.attn2(x, encoder_hidden_states=encoder_hidden_states, attention_mask=encoder_attention_mask,
                                residual_inout=h.contiguous(), **kw2)
