@@ -270,7 +270,7 @@ template <int NP>
 __global__ void __launch_bounds__(256) add_layernorm16_kernel(const uint4* __restrict__ A, const uint4* __restrict__ Bm, const void* __restrict__ gamma,
                                                              const void* __restrict__ beta, int w_f32, uint4* __restrict__ Ysum,
                                                              uint4* __restrict__ Yln, int rows, int C8, float eps, int fmt) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // blockDim.x / 32 rows per CTA
     if (row >= rows) return;
     const size_t base = static_cast<size_t>(row) * C8;
     uint4 a[NP], b[NP];
@@ -437,17 +437,18 @@ int apx_add_layernorm(const void* a, const void* b, const void* gamma, const voi
                 APX_EINVAL, "apx_add_layernorm: pointers must be 16-byte aligned");
     const int C8 = C / 8, np = (C8 + 31) / 32;
     const int fmt = dtype == APX_F16 ? 0 : 1, wf = w_dtype == APX_F32 ? 1 : 0;
-    const dim3 grid(static_cast<unsigned>((rows + 7) / 8));
+    const int rpc = 8;   // rows (warps) per CTA; 1 / 2 / 8 measure the same in the step (8.346 / 8.343 / 8.361 ms, profiles/r3p_bench_b1_addln_rows_*.json)
+    const dim3 grid(static_cast<unsigned>((rows + rpc - 1) / rpc));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint4 *A = static_cast<const uint4*>(a), *Bm = static_cast<const uint4*>(b);
     uint4 *Ys = static_cast<uint4*>(y_sum), *Yl = static_cast<uint4*>(y_ln);
     const int r = static_cast<int>(rows);
     switch (np) {
-        case 1: add_layernorm16_kernel<1><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
-        case 2: add_layernorm16_kernel<2><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
-        case 3: add_layernorm16_kernel<3><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
-        case 4: add_layernorm16_kernel<4><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
-        default: add_layernorm16_kernel<8><<<grid, 256, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 1: add_layernorm16_kernel<1><<<grid, 32 * rpc, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 2: add_layernorm16_kernel<2><<<grid, 32 * rpc, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 3: add_layernorm16_kernel<3><<<grid, 32 * rpc, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        case 4: add_layernorm16_kernel<4><<<grid, 32 * rpc, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
+        default: add_layernorm16_kernel<8><<<grid, 32 * rpc, 0, st>>>(A, Bm, gamma, beta, wf, Ys, Yl, r, C8, eps, fmt); break;
     }
     APX_LAUNCH_CHECK("add_layernorm16_kernel");
     return APX_OK;
