@@ -70,6 +70,13 @@ class AttnProcessor2_0(nn.Module):
             raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
         self._cat = None
 
+    def invalidate_cache(self):
+        """Drop the concatenated / LayerNorm-folded projection weights, the cached context K / V, the prepared mask and the fp32
+        bias copy (all keyed on tensor identity + ``_version``; needed after edits that do not bump the version)."""
+        self._cat = None
+        for name in ("_fold", "_kv", "_mk", "_bo"):
+            self.__dict__.pop(name, None)
+
     def _cat_weight(self, mods):
         # keyed on the weight tensors themselves (kept referenced, so an address cannot be recycled under the cache) + versions
         ws = tuple(m.weight for m in mods)
@@ -304,9 +311,12 @@ class IPAttnProcessor2_0(nn.Module):
         return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
 
     def invalidate_cache(self):
+        """Drop every derived copy (context K/V blob, packed weights, folded-norm pack, fp32 bias): call after edits that do not bump
+        ``_version`` (``param.data`` writes, raw kernels, graph replays into a keyed tensor)."""
         self._ctx_cache = None
         self._w_cache = None
         self._wln_cache = None
+        self._bo_cache = None
 
     def _site_weights(self, attn, heads: int, dtype: torch.dtype):
         """(to_q.weight, to_out[0].weight, packed blob) in the kernel dtype; the blob is the one-time re-layout the

@@ -163,6 +163,9 @@ class APAdapterDenoiser(nn.Module):
         """Drop the captured step graph (and the processors' context / weight caches it points into).  Needed only after edits
         the cache keys cannot see: a context rewritten in place by a raw kernel or a captured graph, ``param.data`` writes."""
         self._graph = None
+        if hasattr(self.unet, "invalidate_caches"):
+            self.unet.invalidate_caches()   # every derived weight copy of the restated UNet + all processors
+            return
         for proc in self._adapter_procs():
             if hasattr(proc, "invalidate_cache"):
                 proc.invalidate_cache()

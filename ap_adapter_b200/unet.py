@@ -745,6 +745,19 @@ class AudioLDM2UNet2DConditionModel(nn.Module):
         for name, module in self.named_children():
             walk(name, module)
 
+    def invalidate_caches(self) -> None:
+        """Drop every derived tensor the inference path keeps next to the weights (fp32 / channels-last copies, concatenated and
+        LayerNorm-folded projections, packed GEGLU weights, the processors' context K/V and packed-weight blobs, additive masks).
+        The caches are keyed on tensor identity + ``_version``; call this after edits the keys cannot see — ``param.data`` writes
+        (8-bit / fused optimisers, EMA copies), raw kernels or graph replays that rewrite a keyed tensor in place."""
+        for m in self.modules():
+            m.__dict__.pop(_CACHE_ATTR, None)
+            if isinstance(m, FeedForward):
+                m._fused = None
+        for proc in self.attn_processors.values():
+            if hasattr(proc, "invalidate_cache"):
+                proc.invalidate_cache()
+
     # ---- forward (modeling_audioldm2.py:663-873) --------------------------------------------------------------
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None,
                 attention_mask=None, cross_attention_kwargs=None, encoder_attention_mask=None, return_dict: bool = False,

@@ -369,3 +369,54 @@ def test_sinc_resample_taps_match_torchaudio():
         taps, orig, new, w = sinc_resample_taps(sr, 16000)
         assert (orig, new, w) == (sr // g, 16000 // g, width) and taps.shape == ref[:, 0, :].shape
         assert (taps - ref[:, 0, :]).abs().max().item() < 1e-5
+
+
+def test_invalidate_caches_drops_every_derived_weight_copy(tiny_unet):
+    """The derived tensors (packed GEGLU weights, concatenated QKV, fp32 copies, additive masks) are keyed on identity + ``_version``;
+    a ``param.data`` write (8-bit / fused optimisers, EMA copies: train_apadapter_v2.py:733-741) is invisible to the key, and
+    ``AudioLDM2UNet2DConditionModel.invalidate_caches`` / ``APAdapterDenoiser.invalidate_graph`` is the documented way to drop them."""
+    import ap_adapter_b200.unet as U
+    from ap_adapter_b200.attention_processor import IPAttnProcessor2_0
+    tiny_unet.set_attn_processor(build_attn_processors(tiny_unet, IPAttnProcessor2_0, ap_scale=0.5))
+    ff = next(m for m in tiny_unet.modules() if isinstance(m, U.FeedForward))
+    attn = next(m for m in tiny_unet.modules() if hasattr(m, "set_processor") and isinstance(m.processor, AttnProcessor2_0))
+    plain = attn.processor
+    conv = tiny_unet.conv_in
+    mask = torch.ones(2, 16)
+
+    w_ff = ff._packed()[0]
+    w_cat = plain._cat_weight((attn.to_q, attn.to_k, attn.to_v))
+    b32 = U._f32(conv, "bias")
+    with torch.no_grad():
+        m0 = tiny_unet._additive_mask(mask, torch.float32, "m0")
+    # versioned in-place edits are seen by the keys ...
+    with torch.no_grad():
+        ff.net[0].proj.weight.mul_(2.0)
+    assert ff._packed()[0] is not w_ff
+    w_ff = ff._packed()[0]
+    # ... `.data` writes are not: the stale copies are served until the caches are dropped
+    ff.net[0].proj.weight.data.mul_(0.5)
+    attn.to_k.weight.data.add_(1.0)
+    conv.bias.data.add_(1.0)
+    assert ff._packed()[0] is w_ff and plain._cat_weight((attn.to_q, attn.to_k, attn.to_v)) is w_cat and U._f32(conv, "bias") is b32
+    den = APAdapterDenoiser(tiny_unet)
+    den._graph = dict(key=None)
+    den.invalidate_graph()
+    assert den._graph is None and plain._cat is None and ff._fused is None
+    assert all(U._CACHE_ATTR not in m.__dict__ for m in tiny_unet.modules())
+    inner = ff.net[0].proj.weight.shape[0] // 2
+    assert torch.equal(ff._packed()[0][0::2], ff.net[0].proj.weight[:inner])
+    assert torch.equal(plain._cat_weight((attn.to_q, attn.to_k, attn.to_v))[inner_rows(attn):2 * inner_rows(attn)], attn.to_k.weight)
+    assert torch.equal(U._f32(conv, "bias"), conv.bias.float())
+    with torch.no_grad():
+        assert tiny_unet._additive_mask(mask, torch.float32, "m0") is not m0
+    for p in tiny_unet.attn_processors.values():
+        if isinstance(p, IPAttnProcessor2_0):
+            assert p._ctx_cache is None and p._w_cache is None and p._wln_cache is None and p._bo_cache is None
+    attn.to_k.weight.data.sub_(1.0)   # the fixture is shared by the module
+    conv.bias.data.sub_(1.0)
+    tiny_unet.invalidate_caches()
+
+
+def inner_rows(attn):
+    return attn.to_q.weight.shape[0]
