@@ -159,12 +159,14 @@ class APAdapterDenoiser(nn.Module):
             g["latents"].copy_(g["out"])
         return g["latents"].clone()
 
-    def invalidate_graph(self):
-        """Drop the captured step graph (and the processors' context / weight caches it points into).  Needed only after edits
-        the cache keys cannot see: a context rewritten in place by a raw kernel or a captured graph, ``param.data`` writes."""
+    def invalidate_graph(self, unet_weights: bool = False):
+        """Drop the captured step graph and the adapter processors' context / weight caches it points into.  Needed only after edits
+        the cache keys cannot see: a context rewritten in place by a raw kernel or a captured graph, ``param.data`` writes to the
+        adapter weights.  ``unet_weights=True`` also drops every derived copy of the (frozen) UNet weights
+        (``AudioLDM2UNet2DConditionModel.invalidate_caches``) — for ``.data`` edits of the UNet itself."""
         self._graph = None
-        if hasattr(self.unet, "invalidate_caches"):
-            self.unet.invalidate_caches()   # every derived weight copy of the restated UNet + all processors
+        if unet_weights and hasattr(self.unet, "invalidate_caches"):
+            self.unet.invalidate_caches()   # includes all processors
             return
         for proc in self._adapter_procs():
             if hasattr(proc, "invalidate_cache"):

@@ -401,7 +401,10 @@ def test_invalidate_caches_drops_every_derived_weight_copy(tiny_unet):
     assert ff._packed()[0] is w_ff and plain._cat_weight((attn.to_q, attn.to_k, attn.to_v)) is w_cat and U._f32(conv, "bias") is b32
     den = APAdapterDenoiser(tiny_unet)
     den._graph = dict(key=None)
-    den.invalidate_graph()
+    den.invalidate_graph()                     # a new prompt: the graph and the adapter sites' caches only
+    assert den._graph is None and ff._packed()[0] is w_ff
+    den._graph = dict(key=None)
+    den.invalidate_graph(unet_weights=True)    # `.data` edits of the UNet: every derived copy
     assert den._graph is None and plain._cat is None and ff._fused is None
     assert all(U._CACHE_ATTR not in m.__dict__ for m in tiny_unet.modules())
     inner = ff.net[0].proj.weight.shape[0] // 2
