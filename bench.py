@@ -109,7 +109,7 @@ def cpu_reference(batch: int, steps: int, warmup: int, budget_s: float) -> dict:
     torch.manual_seed(0)
     unet = AudioLDM2UNet2DConditionModel().eval()
     if ref_shims.reference_processors_available():
-        # oracle/_ref: the reference's OWN IPAttnProcessor2_0 / AttnProcessor2_0 classes (unmodified attention_processor.py) at the
+        # oracle/_ref: the reference's OWN IPAttnProcessor2_0 / AttnProcessor2_0 classes (its attention_processor module, compiled by oracle/build_ref.py) at the
         # 256 sites; only the UNet around them is the restated host graph (diffusers is absent from this image)
         ap = ref_shims.load_attention_processor()
         ip_cls, plain_cls, procs = ap.IPAttnProcessor2_0, ap.AttnProcessor2_0, "reference classes (oracle/_ref)"

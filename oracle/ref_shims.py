@@ -3,10 +3,12 @@
 Used by ``oracle/gen_golden.py`` (and by tests that run only when /root/reference is present) to execute the
 reference itself: ``APadapter/ap_adapter/attention_processor.py`` imports cleanly; ``audio_encoder/*.py`` need
 ``sys.modules`` shims for ``timm`` (restated Block / to_2tuple), ``librosa`` and ``matplotlib``, none of which
-is installed here.  Nothing from the reference is copied — the modules are loaded from where they lie.
+is installed here.  Nothing from the reference is copied — the modules are loaded from where they lie (on a box without the
+tree: from the bytecode ``oracle/build_ref.py`` compiled out of it).
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -18,7 +20,7 @@ import torch.nn as nn
 REF_ROOT = os.environ.get("APX_REFERENCE_ROOT", "/root/reference")
 
 
-REF_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py puts the processor module here
+REF_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py compiles the processor module into here
 
 
 def reference_available() -> bool:
@@ -26,13 +28,22 @@ def reference_available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py"))
 
 
+def _built_module_ok(path: str) -> bool:
+    """oracle/_ref/attention_processor.pyc exists and was compiled by this interpreter's bytecode version."""
+    try:
+        with open(path, "rb") as f:
+            return f.read(4) == importlib.util.MAGIC_NUMBER
+    except OSError:
+        return False
+
+
 def processor_module_path() -> str | None:
-    """The reference's attention_processor.py: from the mounted tree, else the unmodified copy under oracle/_ref."""
-    for path in (os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py"),
-                 os.path.join(REF_BUILT, "attention_processor.py")):
-        if os.path.isfile(path):
-            return path
-    return None
+    """The reference's attention_processor: the source in the mounted tree, else the module compiled from it under oracle/_ref."""
+    src = os.path.join(REF_ROOT, "APadapter", "ap_adapter", "attention_processor.py")
+    if os.path.isfile(src):
+        return src
+    built = os.path.join(REF_BUILT, "attention_processor.pyc")
+    return built if _built_module_ok(built) else None
 
 
 def reference_processors_available() -> bool:
@@ -40,7 +51,8 @@ def reference_processors_available() -> bool:
 
 
 def _load(name: str, path: str):
-    spec = importlib.util.spec_from_file_location(name, path)
+    loader = importlib.machinery.SourcelessFileLoader(name, path) if path.endswith(".pyc") else None
+    spec = importlib.util.spec_from_file_location(name, path, loader=loader)
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
@@ -51,7 +63,7 @@ def load_attention_processor():
     """The reference's attention_processor module (IPAttnProcessor2_0, AttnProcessor2_0, ...)."""
     path = processor_module_path()
     if path is None:
-        raise FileNotFoundError("neither /root/reference nor oracle/_ref holds attention_processor.py (run oracle/build_ref.py)")
+        raise FileNotFoundError("neither /root/reference nor oracle/_ref holds the attention_processor module (run oracle/build_ref.py)")
     return sys.modules.get("apx_ref_attention_processor") or _load("apx_ref_attention_processor", path)
 
 

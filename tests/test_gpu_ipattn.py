@@ -58,7 +58,7 @@ def test_site_matches_oracle(name, dtype):
 @pytest.mark.skipif(not ref_shims.reference_processors_available(), reason="oracle/_ref not built (oracle/build_ref.py)")
 @pytest.mark.parametrize("name", ["cfg1", "site256_real", "site384", "site640"])
 def test_site_matches_the_reference_class_itself(name):
-    """libapx against the reference's OWN IPAttnProcessor2_0 class (oracle/_ref: the unmodified attention_processor.py), run in
+    """libapx against the reference's OWN IPAttnProcessor2_0 class (oracle/_ref: its attention_processor module, compiled from the unmodified source), run in
     fp32 on the CPU of this box on the same fp16-rounded operands — no restatement in between.  Bar: the north star's 1e-3
     (the real-weight site is held to the stock fp16 path's own distance, as in test_site_matches_oracle)."""
     if name not in cases.IPATTN_CASES:

@@ -101,18 +101,24 @@ def test_oracle_against_live_reference_processor():
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(ref_shims.REF_BUILT, "MANIFEST.json")), reason="oracle/_ref not built (oracle/build_ref.py)")
-def test_oracle_ref_is_the_unmodified_reference_module():
-    """oracle/_ref holds the reference's processor module byte for byte: the recorded sha256 matches the file and, where the
-    reference tree is mounted, the file it was taken from."""
+def test_oracle_ref_is_built_from_the_unmodified_reference_module():
+    """oracle/_ref holds the reference's processor module as compiled by CPython from where it lies — build outputs only, no source:
+    the recorded sha256 matches the output, the bytecode is this interpreter's, and where the reference tree is mounted the source it
+    was compiled from is still the file on disk.  The compiled module then loads without the tree and defines the reference classes."""
     import hashlib
+    import importlib.util
     import json
 
     with open(os.path.join(ref_shims.REF_BUILT, "MANIFEST.json")) as f:
         manifest = json.load(f)
+    assert manifest["python_magic"] == importlib.util.MAGIC_NUMBER.hex()
+    assert not [n for n in os.listdir(ref_shims.REF_BUILT) if n.endswith(".py")], "oracle/_ref must not hold reference sources"
     for name, rec in manifest["files"].items():
         with open(os.path.join(ref_shims.REF_BUILT, name), "rb") as f:
             assert hashlib.sha256(f.read()).hexdigest() == rec["sha256"], name
         src = os.path.join(ref_shims.REF_ROOT, rec["from"])
         if os.path.isfile(src):
             with open(src, "rb") as f:
-                assert hashlib.sha256(f.read()).hexdigest() == rec["sha256"], src
+                assert hashlib.sha256(f.read()).hexdigest() == rec["source_sha256"], src
+    mod = ref_shims._load("apx_ref_attention_processor_built", os.path.join(ref_shims.REF_BUILT, "attention_processor.pyc"))
+    assert hasattr(mod, "IPAttnProcessor2_0") and hasattr(mod, "AttnProcessor2_0")
