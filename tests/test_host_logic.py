@@ -423,3 +423,29 @@ def test_invalidate_caches_drops_every_derived_weight_copy(tiny_unet):
 
 def inner_rows(attn):
     return attn.to_q.weight.shape[0]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_layernorm_fold_constants_reproduce_layernorm_then_linear(dtype):
+    """``_lib.fold_layernorm`` is host arithmetic: with Wg = W * gamma (rounded to the kernel dtype), c1 = rowsum(Wg), c2 = W beta + b the
+    GEMM epilogue's ``rstd * (x Wg^T - mean * c1) + c2`` is LayerNorm(x) W^T + b (norm1 / norm2 / norm3 of BasicTransformerBlock in front
+    of to_q / to_k / to_v and the GEGLU projection: modeling_audioldm2 call sites 1140-1156).  Checked in fp64 on the CPU against
+    torch's own layer_norm + linear, with the rounded Wg on both sides so that only the algebra is tested."""
+    from ap_adapter_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    m, k, n, eps = 37, 320, 96, 1e-5
+    x = (torch.randn(m, k, generator=g) * 1.5 + 0.7).to(dtype)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(dtype)
+    b = torch.randn(n, generator=g) * 0.2
+    gamma, beta = 1.0 + 0.3 * torch.randn(k, generator=g), 0.2 * torch.randn(k, generator=g)
+    wg, c1, c2 = _lib.fold_layernorm(w, b, gamma, beta)
+    assert wg.dtype == dtype and c1.dtype == torch.float32 and c2.dtype == torch.float32 and c1.shape == (n,) and c2.shape == (n,)
+    xd = x.double()
+    mean, var = xd.mean(dim=1, keepdim=True), xd.var(dim=1, unbiased=False, keepdim=True)
+    folded = (var + eps).rsqrt() * (xd @ wg.double().t() - mean * c1.double()) + c2.double()
+    # the same function with the rounded, gamma-scaled weight un-folded: LN without affine, then Wg, then the beta / bias term
+    ref = torch.nn.functional.layer_norm(xd, (k,), None, None, eps) @ wg.double().t() + (w.double() @ beta.double() + b.double())
+    assert ((folded - ref).abs().max() / ref.abs().max()).item() < 1e-6
+    # and against the unrounded module chain it stays within the rounding of Wg
+    full = torch.nn.functional.linear(torch.nn.functional.layer_norm(xd, (k,), gamma.double(), beta.double(), eps), w.double(), b.double())
+    assert ((folded - full).abs().max() / full.abs().max()).item() < (2e-3 if dtype == torch.float16 else 1.5e-2)
