@@ -93,3 +93,29 @@ def test_cpu_tensors_fail_loudly():
     attn = StubAttention(256, 768, 8)
     with torch.no_grad(), pytest.raises(_lib.ApxError, match="no CPU fallback"):
         proc(attn, torch.randn(2, 16, 256), encoder_hidden_states=torch.randn(2, 16, 768))
+
+
+def test_site_kernel_policy_is_consistent_over_the_shape_space():
+    """Host-side sweep (no launch): whatever `apx_ipattn_site_kernel` picks for (Bc, S, C, H, Lt, La) is a form that exists for that shape —
+    a fused choice implies `apx_ipattn_fused_ok` and a packed-weight blob — and the size queries answer for every shape the UNet /
+    the training collate can produce (C = 256 / 384 / 640, 8 heads, 8 text tokens, La = 8 ... 512: attention_processor.py:400-403,
+    train_apadapter_v2.py:445-446)."""
+    import itertools
+    lib = _lib.load()
+    seen = set()
+    for c, h in itertools.product(range(64, 1281, 64), (1, 2, 4, 8, 16)):
+        pack = lib.apx_ipattn_pack_bytes(c, h)
+        for lt, la in itertools.product((0, 1, 8, 16, 77), (0, 1, 8, 32, 113, 128, 200, 248, 256, 512)):
+            if lt + la == 0:
+                continue
+            fused = lib.apx_ipattn_fused_ok(c, h, lt, la)
+            for bc, s in itertools.product((1, 2, 16), (1, 64, 252, 1000, 4096)):
+                k = lib.apx_ipattn_site_kernel(bc, s, c, h, lt, la)
+                assert k in (_lib.APX_SITE_AUTO, _lib.APX_SITE_ALLHEADS, _lib.APX_SITE_ONEHEAD), (bc, s, c, h, lt, la, k)
+                assert k == 0 or (fused == 1 and pack > 0), (bc, s, c, h, lt, la, k, fused, pack)
+                seen.add(k)
+    assert seen == {0, 1, 2}
+    for c, la in itertools.product((256, 384, 640), (8, 32, 128, 512)):
+        assert lib.apx_ctx_kv_bytes(16, 8, la, c, 8) >= 16 * 2 * (8 + la) * c * 2
+        assert lib.apx_ctx_kv_workspace_bytes(16, 8, la, c) > 0 and lib.apx_ipattn_workspace_bytes(16, 1000, c) > 0
+        assert lib.apx_ipattn_bwd_workspace_bytes(16, 1000, c, la) > 0
