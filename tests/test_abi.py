@@ -119,3 +119,23 @@ def test_site_kernel_policy_is_consistent_over_the_shape_space():
         assert lib.apx_ctx_kv_bytes(16, 8, la, c, 8) >= 16 * 2 * (8 + la) * c * 2
         assert lib.apx_ctx_kv_workspace_bytes(16, 8, la, c) > 0 and lib.apx_ipattn_workspace_bytes(16, 1000, c) > 0
         assert lib.apx_ipattn_bwd_workspace_bytes(16, 1000, c, la) > 0
+
+
+def test_every_compute_entry_rejects_null_arguments_before_touching_the_device():
+    """Error behaviour of the boundary: every compute entry point of include/apx.h validates its arguments on the host and returns
+    APX_EINVAL (1) with a message naming itself — nothing is dereferenced, nothing is launched, nothing throws across the ABI
+    (runs here without a GPU)."""
+    lib = _lib.load()
+    queries = {"apx_last_error", "apx_version", "apx_device_ok", "apx_set_impl", "apx_get_impl", "apx_set_site_variant", "apx_launch_count",
+               "apx_ipattn_fused_ok", "apx_ipattn_site_kernel"}
+    checked = 0
+    for name, (_res, argtypes) in _lib.SYMBOLS.items():
+        if name in queries or name.endswith("_bytes"):
+            continue
+        args = [None if t in (ctypes.c_void_p, ctypes.c_char_p) else 1.0 if t in (ctypes.c_float, ctypes.c_double) else 0 for t in argtypes]
+        rc = getattr(lib, name)(*args)
+        msg = lib.apx_last_error().decode()
+        assert rc == 1, (name, rc, msg)
+        assert msg.startswith("apx_") and ("null pointer" in msg or "bad argument" in msg), (name, msg)
+        checked += 1
+    assert checked >= 20
