@@ -132,7 +132,8 @@ def test_every_compute_entry_rejects_null_arguments_before_touching_the_device()
     for name, (_res, argtypes) in _lib.SYMBOLS.items():
         if name in queries or name.endswith("_bytes"):
             continue
-        args = [None if t in (ctypes.c_void_p, ctypes.c_char_p) else 1.0 if t in (ctypes.c_float, ctypes.c_double) else 0 for t in argtypes]
+        args = [None if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes._Pointer)
+                else 1.0 if t in (ctypes.c_float, ctypes.c_double) else 0 for t in argtypes]
         rc = getattr(lib, name)(*args)
         msg = lib.apx_last_error().decode()
         assert rc == 1, (name, rc, msg)
