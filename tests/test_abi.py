@@ -140,3 +140,28 @@ def test_every_compute_entry_rejects_null_arguments_before_touching_the_device()
         assert msg.startswith("apx_") and ("null pointer" in msg or "bad argument" in msg), (name, msg)
         checked += 1
     assert checked >= 20
+
+
+def test_error_codes_by_class_for_bad_shapes():
+    """include/apx.h: APX_EINVAL (1) for arguments that are wrong whatever the kernel, APX_EUNSUPPORTED (2) for shapes / dtypes outside
+    what the sm_100a kernels implement, APX_EWORKSPACE (4) for a short caller workspace — all decided on the host, before any launch
+    (non-null dummy pointers are never dereferenced on these paths; runs without a GPU)."""
+    lib = _lib.load()
+    p = ctypes.c_void_p(0x10000)
+    EINVAL, EUNSUPPORTED, EWORKSPACE = 1, 2, 4
+
+    def fwd(bc, s, c, h, lt, la, dtype=0, wsb=1 << 24):
+        return lib.apx_ipattn_fwd(p, p, p, p, None, p, p, bc, s, c, h, lt, la, 0.5, dtype, p, wsb, None)
+
+    assert fwd(2, 64, 250, 8, 8, 8) == EINVAL and b"bad shape" in lib.apx_last_error()          # C % H != 0
+    assert fwd(0, 64, 256, 8, 8, 8) == EINVAL
+    assert fwd(2, 64, 256, 8, 0, 0) == EINVAL                                                     # no context tokens at all
+    assert fwd(2, 64, 256, 8, 8, 8, dtype=7) == EUNSUPPORTED and b"dtype" in lib.apx_last_error()
+    assert fwd(2, 64, 256, 8, 8, 8, wsb=16) == EWORKSPACE and b"workspace" in lib.apx_last_error()
+    ln = lambda a, rows, c: lib.apx_add_layernorm(a, None, p, p, 0, None, p, rows, c, 1e-5, 0, None)  # noqa: E731
+    assert ln(p, 10, 100) == EUNSUPPORTED and ln(p, 10, 4096) == EUNSUPPORTED
+    assert ln(ctypes.c_void_p(0x10004), 10, 256) == EINVAL and b"aligned" in lib.apx_last_error()
+    gn = lambda c, groups: lib.apx_groupnorm_nhwc(p, p, p, None, None, 0, p, 2, 100, c, groups, 1e-5, 1, 0, None)  # noqa: E731
+    assert gn(250, 32) == EINVAL and gn(64, 32) == EUNSUPPORTED
+    assert lib.apx_flash_attention(p, 0, 192, p, 0, 192, p, 0, 192, p, 0, 192, 1, 64, 64, 192, 8, 0, None) == EUNSUPPORTED   # d = 24
+    assert b"head dim 24" in lib.apx_last_error()
