@@ -122,3 +122,52 @@ def test_oracle_ref_is_built_from_the_unmodified_reference_module():
                 assert hashlib.sha256(f.read()).hexdigest() == rec["source_sha256"], src
     mod = ref_shims._load("apx_ref_attention_processor_built", os.path.join(ref_shims.REF_BUILT, "attention_processor.pyc"))
     assert hasattr(mod, "IPAttnProcessor2_0") and hasattr(mod, "AttnProcessor2_0")
+
+
+def test_restated_timm_block_matches_an_independent_vit_implementation():
+    """timm is absent from this image, so the ``Block`` the reference imports (``audio_encoder/models_mae.py:18``) is restated from its
+    published forward both in the oracle (``audiomae_oracle.vit_block``) and in the shim the goldens were generated with
+    (``ref_shims``; the two agree to 1e-5 through the fixtures).  This pins that restatement to an implementation we did not write:
+    Hugging Face transformers' ``ViTLayer`` — the port of timm's ViT block (pre-LN, qkv with bias, softmax(q k^T / sqrt(d)) v, proj,
+    erf-GELU MLP, residuals) — given the same weights (the fused qkv matrix split into query / key / value) and eps = 1e-6."""
+    vit = pytest.importorskip("transformers.models.vit.modeling_vit")
+    from transformers import ViTConfig
+
+    from oracle import audiomae_oracle as ao
+    from oracle import cases
+
+    sd = cases.mae_state_dict(depth=2)
+    c = ao.EMBED
+    cfg = ViTConfig(hidden_size=c, num_attention_heads=ao.HEADS, intermediate_size=ao.MLP, hidden_act="gelu", layer_norm_eps=ao.LN_EPS,
+                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, qkv_bias=True)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(11)
+    x = torch.randn(2, 513, c)
+    for i in range(2):
+        p = f"blocks.{i}."
+        layer = vit.ViTLayer(cfg).eval()
+        qw, qb = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+        mapping = {"attention.attention.query": (qw[:c], qb[:c]), "attention.attention.key": (qw[c:2 * c], qb[c:2 * c]),
+                   "attention.attention.value": (qw[2 * c:], qb[2 * c:]),
+                   "attention.output.dense": (sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]),
+                   "intermediate.dense": (sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]),
+                   "output.dense": (sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]),
+                   "layernorm_before": (sd[p + "norm1.weight"], sd[p + "norm1.bias"]),
+                   "layernorm_after": (sd[p + "norm2.weight"], sd[p + "norm2.bias"])}
+        with torch.no_grad():
+            for name, (w, b) in mapping.items():
+                mod = layer.get_submodule(name)
+                mod.weight.copy_(w)
+                mod.bias.copy_(b)
+            y_hf = layer(x)
+            y_hf = y_hf[0] if isinstance(y_hf, tuple) else y_hf
+            y = ao.vit_block(x, sd, i)
+        assert (y - x).abs().max() > 0.5                                     # the block does something at these weights
+        assert ((y - y_hf).abs().max() / y_hf.abs().max()).item() < 1e-6     # measured: bitwise equal
+        # the check can tell the details apart: a LayerNorm eps of 1e-3 in place of the reference's 1e-6 is seen
+        with torch.no_grad():
+            layer.layernorm_before.eps = 1e-3
+            y_off = layer(x)
+            y_off = y_off[0] if isinstance(y_off, tuple) else y_off
+        assert ((y - y_off).abs().max() / y_hf.abs().max()).item() > 1e-5
+        x = y
